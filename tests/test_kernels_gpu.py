@@ -1,0 +1,330 @@
+"""Kernel-level parity on a B200: every C-ABI launcher against a plain PyTorch fp32 restatement of the same op
+(bf16-rounded operands, fp32 math, TF32 off).  Tolerances are written next to each check."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    from tts_indic_server_f5_b200 import ops
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+
+DEV = "cuda"
+
+
+def rnd(*shape, seed=0, scale=1.0, dtype=torch.float32):
+    g = torch.Generator("cpu").manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(DEV).to(dtype)
+
+
+def rel_err(a, b):
+    return ((a.float() - b.float()).norm() / b.float().norm().clamp_min(1e-20)).item()
+
+
+def check(name, got, want, rel, amax=None):
+    r = rel_err(got, want)
+    m = (got.float() - want.float()).abs().max().item()
+    print(f"[{name}] rel-L2 {r:.3e} max-abs {m:.3e} (ref max {want.float().abs().max().item():.3e})")
+    assert math.isfinite(r) and r <= rel, f"{name}: rel-L2 {r:.3e} > {rel:.1e} (max-abs {m:.3e})"
+    if amax is not None:
+        assert m <= amax, f"{name}: max-abs {m:.3e} > {amax:.1e}"
+
+
+@pytest.mark.parametrize("M,N,K,bn", [(128, 256, 64, 256), (300, 256, 256, 256), (1000, 3072, 1024, 256),
+                                      (515, 1024, 2048, 128), (257, 128, 128, 128), (130, 64, 192, 64),
+                                      (200, 104, 128, 128), (4096, 2048, 1024, 256)])
+def test_gemm_store_bf16(M, N, K, bn):
+    A = rnd(M, K, seed=1, dtype=torch.bfloat16)
+    B = rnd(N, K, seed=2, scale=1 / math.sqrt(K), dtype=torch.bfloat16)
+    bias = rnd(N, seed=3)
+    out = torch.full((M, N), 7.0, device=DEV, dtype=torch.bfloat16)
+    ops.gemm(A, B, mode=ops.F5_EPI_STORE_BF16, bias=bias, out=out, block_n=bn)
+    torch.cuda.synchronize()
+    ref = A.float() @ B.float().t() + bias
+    check(f"gemm_bf16 {M}x{N}x{K}/{bn}", out, ref, rel=4e-3)   # bf16 output rounding: 2^-9 relative
+
+
+@pytest.mark.parametrize("act", [0, 1, 2, 3])
+def test_gemm_store_f32_addend_mask_act(act):
+    M, N, K = 777, 512, 320
+    A = rnd(M, K, seed=4, dtype=torch.bfloat16)
+    B = rnd(N, K, seed=5, scale=1 / math.sqrt(K), dtype=torch.bfloat16)
+    bias, add = rnd(N, seed=6), rnd(M, N, seed=7)
+    row_pos = torch.arange(M, device=DEV, dtype=torch.int32)
+    row_pos[100:116] = -1
+    out = torch.zeros(M, N, device=DEV)
+    out2 = torch.full((M, N), 3.0, device=DEV, dtype=torch.bfloat16)
+    ops.gemm(A, B, mode=ops.F5_EPI_STORE_F32, act=act, bias=bias, out=out, out2=out2, addend=add, row_pos=row_pos,
+             mask_rows=True)
+    torch.cuda.synchronize()
+    z = A.float() @ B.float().t() + bias
+    z = [z, F.gelu(z, approximate="tanh"), F.gelu(z), F.mish(z)][act] + add
+    check(f"gemm_f32 act{act}", out, z, rel=2e-5, amax=2e-4)   # fp32 accumulate, different summation order
+    zm = z.clone()
+    zm[100:116] = 0
+    check(f"gemm_f32 act{act} bf16 copy", out2, zm, rel=4e-3)
+
+
+def test_gemm_resid_gate():
+    M, N, K = 640, 1024, 1024
+    A = rnd(M, K, seed=8, dtype=torch.bfloat16)
+    B = rnd(N, K, seed=9, scale=1 / math.sqrt(K), dtype=torch.bfloat16)
+    bias, gate, x0 = rnd(N, seed=10), rnd(N, seed=11), rnd(M, N, seed=12)
+    x = x0.clone()
+    ops.gemm(A, B, mode=ops.F5_EPI_RESID_F32, bias=bias, gate=gate, resid=x)
+    torch.cuda.synchronize()
+    check("gemm_resid", x, x0 + gate * (A.float() @ B.float().t() + bias), rel=2e-5, amax=3e-4)
+    x = x0.clone()
+    ops.gemm(A, B, mode=ops.F5_EPI_RESID_F32, act=ops.F5_ACT_MISH, bias=bias, resid=x)
+    torch.cuda.synchronize()
+    check("gemm_resid_mish_nogate", x, x0 + F.mish(A.float() @ B.float().t() + bias), rel=2e-5, amax=3e-4)
+
+
+def test_gemm_qkv_rope():
+    D, M = 256, 400
+    A = rnd(M, D, seed=13, dtype=torch.bfloat16)
+    B = rnd(3 * D, D, seed=14, scale=1 / math.sqrt(D), dtype=torch.bfloat16)
+    bias = rnd(3 * D, seed=15)
+    pos = torch.cat([torch.arange(150), torch.full((16,), -1), torch.arange(234)]).to(DEV).to(torch.int32)
+    inv = 1.0 / (10000.0 ** (torch.arange(0, 64, 2).float() / 64))
+    ang = torch.arange(4096).float()[:, None] * inv[None]
+    rope = torch.stack((ang.cos(), ang.sin()), dim=-1).reshape(4096, 64).contiguous().to(DEV)
+    out = torch.zeros(M, 3 * D, device=DEV, dtype=torch.bfloat16)
+    ops.gemm(A, B, mode=ops.F5_EPI_STORE_BF16, bias=bias, out=out, row_pos=pos, rope=rope, rope_period=D, rope_tiles=2)
+    torch.cuda.synchronize()
+    z = A.float() @ B.float().t() + bias
+    live = pos >= 0
+    ref = z.clone()
+    for base in (0, D):
+        blk = z[:, base:base + 64]
+        c, s = ang.to(DEV)[pos.clamp_min(0).long()].cos(), ang.to(DEV)[pos.clamp_min(0).long()].sin()
+        x0, x1 = blk[:, 0::2], blk[:, 1::2]
+        rot = torch.stack((x0 * c - x1 * s, x1 * c + x0 * s), dim=-1).reshape(M, 64)
+        ref[:, base:base + 64] = torch.where(live[:, None], rot, blk)
+    check("gemm_qkv_rope", out[live], ref[live], rel=4e-3)
+
+
+def test_gemm_grouped_conv31():
+    C, G, Kw, n1, n2, gap = 256, 4, 31, 150, 230, 16
+    M = gap + n1 + gap + n2 + gap
+    x = torch.zeros(M, C, device=DEV)
+    x[gap:gap + n1] = rnd(n1, C, seed=16)
+    x[2 * gap + n1:2 * gap + n1 + n2] = rnd(n2, C, seed=17)
+    xb = x.to(torch.bfloat16)
+    w = rnd(C, C // G, Kw, seed=18, scale=1 / math.sqrt(C // G * Kw))
+    bias = rnd(C, seed=19)
+    wt = w.permute(2, 0, 1).contiguous().reshape(Kw * C, C // G).to(torch.bfloat16)   # [tap][out][in]
+    pos = torch.full((M,), -1, dtype=torch.int32)
+    pos[gap:gap + n1] = torch.arange(n1)
+    pos[2 * gap + n1:2 * gap + n1 + n2] = torch.arange(n2)
+    pos = pos.to(DEV)
+    out = torch.full((M, C), 5.0, device=DEV, dtype=torch.bfloat16)
+    ops.gemm(xb, wt, M=M, N=C, mode=ops.F5_EPI_STORE_BF16, act=ops.F5_ACT_MISH, bias=bias, out=out, row_pos=pos,
+             mask_rows=True, block_n=64, num_taps=Kw, kc_per_tap=1, tap_pad=Kw // 2, a_grouped=True, b_tap_rows=C)
+    torch.cuda.synchronize()
+    wq = wt.float().reshape(Kw, C, C // G).permute(1, 2, 0).contiguous()
+    for s0, n in ((gap, n1), (2 * gap + n1, n2)):
+        ref = F.mish(F.conv1d(xb[s0:s0 + n].float().t()[None], wq, bias, padding=Kw // 2, groups=G))[0].t()
+        check(f"conv31 seg@{s0}", out[s0:s0 + n], ref, rel=4e-3)
+    assert out[:gap].abs().max().item() == 0 and out[gap + n1:2 * gap + n1].abs().max().item() == 0
+
+
+def test_gemm_dense_conv7():
+    Cin, Cin_pad, Cout, Kw, n, gap = 100, 128, 512, 7, 333, 3
+    M = gap + n + gap
+    x = torch.zeros(M, Cin_pad, device=DEV)
+    x[gap:gap + n, :Cin] = rnd(n, Cin, seed=20)
+    xb = x.to(torch.bfloat16)
+    w = rnd(Cout, Cin, Kw, seed=21, scale=1 / math.sqrt(Cin * Kw))
+    bias = rnd(Cout, seed=22)
+    wt = torch.zeros(Kw, Cout, Cin_pad, device=DEV)
+    wt[:, :, :Cin] = w.permute(2, 0, 1)
+    wt = wt.reshape(Kw * Cout, Cin_pad).to(torch.bfloat16)
+    out = torch.zeros(M, Cout, device=DEV)
+    ops.gemm(xb, wt, M=M, N=Cout, mode=ops.F5_EPI_STORE_F32, bias=bias, out=out, num_taps=Kw, kc_per_tap=2,
+             tap_pad=3, b_tap_rows=Cout)
+    torch.cuda.synchronize()
+    wq = wt.float().reshape(Kw, Cout, Cin_pad)[:, :, :Cin].permute(1, 2, 0).contiguous()
+    ref = F.conv1d(xb[gap:gap + n, :Cin].float().t()[None], wq, bias, padding=3)[0].t()
+    check("conv7 dense", out[gap:gap + n], ref, rel=2e-5, amax=2e-4)
+
+
+def _attn_case(lens, H, variant, scale_q=1.0, seed=30):
+    D = H * 64
+    gap = 16
+    starts, rows = [], gap
+    for n in lens:
+        starts.append(rows)
+        rows += n + gap
+    rows = (rows + 127) // 128 * 128
+    qkv = rnd(rows, 3 * D, seed=seed, dtype=torch.bfloat16)
+    qkv[:, :D] *= scale_q
+    tiles = []
+    for s0, n in zip(starts, lens):
+        for q0 in range(0, n, 128):
+            tiles.append([s0 + q0, s0, n, min(128, n - q0)])
+    tiles = torch.tensor(tiles, dtype=torch.int32, device=DEV)
+    out = torch.zeros(rows, D, device=DEV, dtype=torch.bfloat16)
+    vt = qkv[:, 2 * D:].t().contiguous() if variant == 1 else None
+    ops.attention(qkv, tiles, out, H, 0, D, 2 * D, 0.125, variant, vt)
+    torch.cuda.synchronize()
+    for s0, n in zip(starts, lens):
+        q, k, v = (qkv[s0:s0 + n, i * D:(i + 1) * D].float().view(n, H, 64).transpose(0, 1) for i in range(3))
+        ref = F.scaled_dot_product_attention(q[None], k[None], v[None])[0].transpose(0, 1).reshape(n, D)
+        check(f"attn v{variant} n={n} H={H} sq={scale_q}", out[s0:s0 + n], ref, rel=1e-2)   # P and O rounded to bf16
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+def test_attention_small(variant):
+    _attn_case([128], 1, variant)
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+def test_attention_ragged(variant):
+    _attn_case([300, 77, 513, 128], 4, variant)
+    _attn_case([785], 16, variant, scale_q=6.0, seed=31)   # peaky softmax exercises the running-max rescale
+
+
+def test_layernorm_mod():
+    for D in (128, 256, 512, 1024):
+        M = 1001
+        x = rnd(M, D, seed=40, scale=3.0) + 1.5
+        a, b = rnd(D, seed=41), rnd(D, seed=42)
+        y = torch.zeros(M, D, device=DEV, dtype=torch.bfloat16)
+        ops.layernorm_mod(x, y, a, b, 1.0)
+        torch.cuda.synchronize()
+        check(f"ln_mod D={D}", y, F.layer_norm(x, (D,), eps=1e-6) * (1 + a) + b, rel=4e-3)
+        ops.layernorm_mod(x, y, a, b, 0.0)
+        torch.cuda.synchronize()
+        check(f"ln_affine D={D}", y, F.layer_norm(x, (D,), a, b, eps=1e-6), rel=4e-3)
+
+
+def test_dwconv7_ln():
+    for C in (128, 512):
+        n1, n2, gap = 100, 57, 5
+        M = gap + n1 + gap + n2 + gap
+        pos = torch.full((M,), -1, dtype=torch.int32)
+        pos[gap:gap + n1] = torch.arange(n1)
+        pos[2 * gap + n1:2 * gap + n1 + n2] = torch.arange(n2)
+        pos = pos.to(DEV)
+        x = rnd(M, C, seed=43)      # garbage in gap rows must not leak
+        w, bias, lw, lb = rnd(C, 7, seed=44, scale=0.4), rnd(C, seed=45), rnd(C, seed=46) + 1, rnd(C, seed=47)
+        y = torch.full((M, C), 9.0, device=DEV, dtype=torch.bfloat16)
+        ops.dwconv7_ln(x, y, pos, w, bias, lw, lb)
+        torch.cuda.synchronize()
+        for s0, n in ((gap, n1), (2 * gap + n1, n2)):
+            h = F.conv1d(x[s0:s0 + n].t()[None], w[:, None, :], bias, padding=3, groups=C)[0].t()
+            check(f"dwconv7_ln C={C}", y[s0:s0 + n], F.layer_norm(h, (C,), lw, lb, eps=1e-6), rel=4e-3)
+        assert y[:gap].abs().max().item() == 0
+
+
+def test_grn():
+    C, segs = 1024, [(3, 200), (220, 77)]
+    x = rnd(300, C, seed=48, dtype=torch.bfloat16)
+    x0 = x.clone()
+    seg = torch.tensor(segs, dtype=torch.int32, device=DEV)
+    sumsq = torch.zeros(len(segs), C, device=DEV)
+    gamma, beta = rnd(C, seed=49), rnd(C, seed=50)
+    ops.grn(x, seg, sumsq, gamma, beta)
+    torch.cuda.synchronize()
+    for s0, n in segs:
+        xs = x0[s0:s0 + n].float()
+        gx = xs.norm(p=2, dim=0, keepdim=True)
+        nx = gx / (gx.mean(dim=-1, keepdim=True) + 1e-6)
+        check("grn", x[s0:s0 + n], gamma * (xs * nx) + beta + xs, rel=4e-3)
+    assert torch.equal(x[:3], x0[:3])
+
+
+def test_gather_pack_where_silu_time():
+    M, C, V = 200, 512, 50
+    ids = torch.randint(0, V, (M,), dtype=torch.int32, device=DEV)
+    pos = torch.arange(M, dtype=torch.int32, device=DEV) - 10
+    emb, table = rnd(V, C, seed=51), rnd(64, C, seed=52)
+    out = torch.full((M, C), 1.0, device=DEV)
+    ops.text_gather_pos(ids, pos, emb, table, out)
+    torch.cuda.synchronize()
+    ref = emb[ids.long()] + table[pos.clamp(0, 63).long()]
+    ref[:10] = 0
+    assert torch.equal(out, ref)
+    src = rnd(M, 100, seed=53)
+    dst = torch.full((M, 256), 2.0, device=DEV, dtype=torch.bfloat16)
+    rows = torch.arange(M, dtype=torch.int32, device=DEV).flip(0).contiguous()
+    rows[5] = -1
+    ops.pack_bf16(src, dst, 128, 100, 128, src_rows=rows)
+    torch.cuda.synchronize()
+    want = torch.zeros(M, 128, device=DEV)
+    want[:, :100] = src[rows.clamp_min(0).long()]
+    want[5] = 0
+    assert torch.equal(dst[:, 128:], want.to(torch.bfloat16)) and (dst[:, :128] == 2).all()
+    x, c = rnd(M, 128, seed=54), rnd(M, 128, seed=55)
+    flag = (torch.arange(M, device=DEV) % 3 == 0).to(torch.int32)
+    x1 = x.clone()
+    ops.where_rows(x1, c, flag, 100)
+    torch.cuda.synchronize()
+    want = x.clone()
+    want[flag.bool(), :100] = c[flag.bool(), :100]
+    assert torch.equal(x1, want)
+    v = rnd(1000, 6144, seed=56)
+    o = torch.zeros(1000, 6144, device=DEV, dtype=torch.bfloat16)
+    ops.silu_bf16(v, o)
+    torch.cuda.synchronize()
+    check("silu", o, F.silu(v), rel=4e-3)
+    t = torch.linspace(0, 1, 33, device=DEV)
+    half = 128
+    freqs = torch.exp(torch.arange(half).float() * -(math.log(10000) / (half - 1))).to(DEV)
+    te = torch.zeros(33, 256, device=DEV, dtype=torch.bfloat16)
+    ops.time_sinus(t, freqs, te)
+    torch.cuda.synchronize()
+    arg = (1000 * t)[:, None] * freqs[None]
+    check("time_sinus", te, torch.cat((arg.sin(), arg.cos()), -1), rel=5e-3)
+
+
+def test_cfg_euler():
+    half, C, Cp = 300, 100, 128
+    x0 = rnd(half, Cp, seed=57)
+    pred = rnd(2 * half, Cp, seed=58)
+    pos = torch.arange(half, dtype=torch.int32, device=DEV)
+    pos[40:56] = -1
+    dts = torch.tensor([0.1, 0.03, 0.2], device=DEV)
+    xb = torch.full((2 * half, Cp), 4.0, device=DEV, dtype=torch.bfloat16)
+    x = x0.clone()
+    ops.cfg_euler(x, pred, half, C, pos, dts, 1, 2.0, xb, Cp)
+    torch.cuda.synchronize()
+    pc, pu = pred[:half, :C], pred[half:, :C]
+    want = x0.clone()
+    live = pos >= 0
+    want[live, :C] = (x0[:, :C] + dts[1] * (pc + (pc - pu) * 2.0))[live]
+    check("cfg_euler x", x, want, rel=1e-6)
+    wb = torch.zeros(half, Cp, device=DEV)
+    wb[live, :C] = want[live, :C]
+    assert torch.equal(xb[:half], wb.to(torch.bfloat16)) and torch.equal(xb[half:], wb.to(torch.bfloat16))
+
+
+def test_istft_vs_torch():
+    segs = [(2, 50), (60, 1), (70, 129)]
+    rows = 210
+    spec = rnd(rows, 1152, seed=59)
+    spec[:, :513] = spec[:, :513] * 1.5 + 0.5      # some magnitudes hit the 1e2 clip
+    window = torch.hann_window(1024, device=DEV)
+    frames = torch.zeros(rows, 1024, device=DEV)
+    offs, tot = [], 0
+    for _, T in segs:
+        offs.append(tot)
+        tot += 256 * (T - 1)
+    seg = torch.tensor([[r0, T, o, 0] for (r0, T), o in zip(segs, offs)], dtype=torch.int32, device=DEV)
+    wav = torch.zeros(max(tot, 1), device=DEV)
+    gains = torch.tensor([1.0, 1.0, 0.5], device=DEV)
+    ops.istft(spec, window, frames, seg, 256 * 128, wav, gains)
+    torch.cuda.synchronize()
+    for (r0, T), o, g in zip(segs, offs, gains.tolist()):
+        if T < 2:
+            continue
+        mag = spec[r0:r0 + T, :513].exp().clip(max=1e2)
+        ph = spec[r0:r0 + T, 513:1026]
+        S = (mag * (ph.cos() + 1j * ph.sin())).t()[None]
+        ref = torch.istft(S, 1024, 256, 1024, window, center=True)[0] * g
+        check(f"istft T={T}", wav[o:o + 256 * (T - 1)], ref, rel=2e-5)

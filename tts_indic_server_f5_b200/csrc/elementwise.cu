@@ -1,0 +1,373 @@
+// Memory-bound kernels of the F5-TTS hot path (sm_100a): fused LayerNorm+modulation, depthwise conv + LayerNorm, GRN,
+// token gather, bf16 packing, CFG+Euler update, time embedding.  All are coalesced / 128-bit vectorised; row-wise
+// reductions use warp shuffles (one warp per row), grids are sized from the row count.
+#include "f5_common.cuh"
+#include "../../include/f5_b200.h"
+
+namespace f5 {
+
+// ------------------------------------------------------------------------------------------------ LayerNorm * a + b -> bf16
+template <int NV>  // float4 per lane: D = NV * 128
+__global__ void __launch_bounds__(256) layernorm_mod_kernel(const float* __restrict__ x, long long ldx,
+                                                            __nv_bfloat16* __restrict__ y, long long ldy, int M,
+                                                            const float* __restrict__ a, const float* __restrict__ b,
+                                                            float a_off, float eps) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const int lane = threadIdx.x & 31;
+  constexpr int D = NV * 128;
+  const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * ldx);
+  float4 v[NV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    v[i] = xr[i * 32 + lane];
+    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+  const float mean = warp_sum(s) * (1.f / D);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float d0 = v[i].x - mean, d1 = v[i].y - mean, d2 = v[i].z - mean, d3 = v[i].w - mean;
+    q += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+  }
+  const float rstd = rsqrtf(warp_sum(q) * (1.f / D) + eps);
+  uint2* yr = reinterpret_cast<uint2*>(y + static_cast<size_t>(row) * ldy);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float4 a4 = reinterpret_cast<const float4*>(a)[i * 32 + lane];
+    const float4 b4 = reinterpret_cast<const float4*>(b)[i * 32 + lane];
+    const float o0 = (v[i].x - mean) * rstd * (a_off + a4.x) + b4.x;
+    const float o1 = (v[i].y - mean) * rstd * (a_off + a4.y) + b4.y;
+    const float o2 = (v[i].z - mean) * rstd * (a_off + a4.z) + b4.z;
+    const float o3 = (v[i].w - mean) * rstd * (a_off + a4.w) + b4.w;
+    yr[i * 32 + lane] = make_uint2(pack_bf16x2(o0, o1), pack_bf16x2(o2, o3));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ dwconv(k=7) + LN -> bf16
+template <int NV>  // C = NV * 128
+__global__ void __launch_bounds__(256) dwconv7_ln_kernel(const float* __restrict__ x, long long ldx,
+                                                         __nv_bfloat16* __restrict__ y, long long ldy, int M,
+                                                         const int* __restrict__ row_pos, const float* __restrict__ w,
+                                                         const float* __restrict__ bias, const float* __restrict__ ln_w,
+                                                         const float* __restrict__ ln_b, float eps) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const int lane = threadIdx.x & 31;
+  constexpr int C = NV * 128;
+  uint2* yr = reinterpret_cast<uint2*>(y + static_cast<size_t>(row) * ldy);
+  const int pos = row_pos[row];
+  if (pos < 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) yr[i * 32 + lane] = make_uint2(0, 0);
+    return;
+  }
+  float4 acc[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) acc[i] = reinterpret_cast<const float4*>(bias)[i * 32 + lane];
+#pragma unroll
+  for (int k = 0; k < 7; ++k) {
+    const int rr = row + k - 3;
+    if (rr < 0 || rr >= M) continue;
+    if (row_pos[rr] != pos + k - 3) continue;  // neighbour belongs to another utterance / gap => zero padding
+    const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(rr) * ldx);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float4 xv = xr[i * 32 + lane];
+      const int c = (i * 32 + lane) * 4;
+      acc[i].x += xv.x * w[(c + 0) * 7 + k];
+      acc[i].y += xv.y * w[(c + 1) * 7 + k];
+      acc[i].z += xv.z * w[(c + 2) * 7 + k];
+      acc[i].w += xv.w * w[(c + 3) * 7 + k];
+    }
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) s += (acc[i].x + acc[i].y) + (acc[i].z + acc[i].w);
+  const float mean = warp_sum(s) * (1.f / C);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float d0 = acc[i].x - mean, d1 = acc[i].y - mean, d2 = acc[i].z - mean, d3 = acc[i].w - mean;
+    q += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+  }
+  const float rstd = rsqrtf(warp_sum(q) * (1.f / C) + eps);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float4 a4 = reinterpret_cast<const float4*>(ln_w)[i * 32 + lane];
+    const float4 b4 = reinterpret_cast<const float4*>(ln_b)[i * 32 + lane];
+    yr[i * 32 + lane] = make_uint2(
+        pack_bf16x2((acc[i].x - mean) * rstd * a4.x + b4.x, (acc[i].y - mean) * rstd * a4.y + b4.y),
+        pack_bf16x2((acc[i].z - mean) * rstd * a4.z + b4.z, (acc[i].w - mean) * rstd * a4.w + b4.w));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ GRN
+constexpr int GRN_ROWS = 32;  // rows per block
+// grid (row chunks of the longest segment, num_segs); block = C/2 threads (bf16x2 per thread)
+__global__ void grn_sumsq_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, int C,
+                                 const int* __restrict__ seg_rows, float* __restrict__ sumsq) {
+  const int seg = blockIdx.y;
+  const int row0 = seg_rows[2 * seg], n = seg_rows[2 * seg + 1];
+  const int r0 = blockIdx.x * GRN_ROWS;
+  if (r0 >= n) return;
+  const int r1 = min(n, r0 + GRN_ROWS);
+  for (int c2 = threadIdx.x; c2 < C / 2; c2 += blockDim.x) {
+    float s0 = 0.f, s1 = 0.f;
+    for (int r = r0; r < r1; ++r) {
+      const __nv_bfloat162 v = reinterpret_cast<const __nv_bfloat162*>(x + static_cast<size_t>(row0 + r) * ldx)[c2];
+      const float2 f = __bfloat1622float2(v);
+      s0 += f.x * f.x;
+      s1 += f.y * f.y;
+    }
+    atomicAdd(&sumsq[static_cast<size_t>(seg) * C + 2 * c2], s0);
+    atomicAdd(&sumsq[static_cast<size_t>(seg) * C + 2 * c2 + 1], s1);
+  }
+}
+
+__global__ void grn_apply_kernel(__nv_bfloat16* __restrict__ x, long long ldx, int C, const int* __restrict__ seg_rows,
+                                 const float* __restrict__ sumsq, const float* __restrict__ gamma,
+                                 const float* __restrict__ beta) {
+  __shared__ float red[32];
+  __shared__ float mean_gx;
+  const int seg = blockIdx.y;
+  const int row0 = seg_rows[2 * seg], n = seg_rows[2 * seg + 1];
+  const int r0 = blockIdx.x * GRN_ROWS;
+  if (r0 >= n) return;
+  const int r1 = min(n, r0 + GRN_ROWS);
+  float part = 0.f;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) part += sqrtf(sumsq[static_cast<size_t>(seg) * C + c]);
+  part = warp_sum(part);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = threadIdx.x < (blockDim.x + 31) / 32 ? red[threadIdx.x] : 0.f;
+    t = warp_sum(t);
+    if (threadIdx.x == 0) mean_gx = t / C;
+  }
+  __syncthreads();
+  const float inv = 1.f / (mean_gx + 1e-6f);
+  for (int c2 = threadIdx.x; c2 < C / 2; c2 += blockDim.x) {
+    const float n0 = sqrtf(sumsq[static_cast<size_t>(seg) * C + 2 * c2]) * inv;
+    const float n1 = sqrtf(sumsq[static_cast<size_t>(seg) * C + 2 * c2 + 1]) * inv;
+    const float g0 = gamma[2 * c2], g1 = gamma[2 * c2 + 1], b0 = beta[2 * c2], b1 = beta[2 * c2 + 1];
+    for (int r = r0; r < r1; ++r) {
+      __nv_bfloat162* p = reinterpret_cast<__nv_bfloat162*>(x + static_cast<size_t>(row0 + r) * ldx) + c2;
+      const float2 f = __bfloat1622float2(*p);
+      *p = __floats2bfloat162_rn(g0 * (f.x * n0) + b0 + f.x, g1 * (f.y * n1) + b1 + f.y);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ gather / pack / misc
+__global__ void text_gather_pos_kernel(const int* __restrict__ ids, const int* __restrict__ row_pos,
+                                       const float* __restrict__ emb, const float* __restrict__ pos_table, int max_pos,
+                                       float* __restrict__ out, long long ldo, int M, int C) {
+  const int row = blockIdx.x;
+  if (row >= M) return;
+  const int pos = row_pos[row];
+  float4* o = reinterpret_cast<float4*>(out + static_cast<size_t>(row) * ldo);
+  if (pos < 0) {
+    for (int c = threadIdx.x; c < C / 4; c += blockDim.x) o[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    return;
+  }
+  const float4* e = reinterpret_cast<const float4*>(emb + static_cast<size_t>(ids[row]) * C);
+  const float4* pt = reinterpret_cast<const float4*>(pos_table + static_cast<size_t>(min(pos, max_pos - 1)) * C);
+  for (int c = threadIdx.x; c < C / 4; c += blockDim.x) {
+    const float4 a = e[c], b = pt[c];
+    o[c] = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+  }
+}
+
+// one warp per row; C_pad % 8 == 0
+__global__ void __launch_bounds__(256) pack_bf16_kernel(const float* __restrict__ src, long long lds,
+                                                        __nv_bfloat16* __restrict__ dst, long long ldd, int dst_col,
+                                                        int M, int C, int C_pad, const int* __restrict__ src_rows,
+                                                        const int* __restrict__ row_pos) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const int lane = threadIdx.x & 31;
+  int srow = src_rows != nullptr ? src_rows[row] : row;
+  if (row_pos != nullptr && row_pos[row] < 0) srow = -1;
+  __nv_bfloat16* d = dst + static_cast<size_t>(row) * ldd + dst_col;
+  const float* s = src + static_cast<size_t>(srow < 0 ? 0 : srow) * lds;
+  for (int c = lane * 2; c < C_pad; c += 64) {
+    const float v0 = (srow >= 0 && c < C) ? s[c] : 0.f;
+    const float v1 = (srow >= 0 && c + 1 < C) ? s[c + 1] : 0.f;
+    *reinterpret_cast<uint32_t*>(d + c) = pack_bf16x2(v0, v1);
+  }
+}
+
+__global__ void where_rows_kernel(float* __restrict__ x, long long ldx, const float* __restrict__ c, long long ldc,
+                                  const int* __restrict__ flag, int M, int C) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= M || flag[row] == 0) return;
+  for (int i = threadIdx.x & 31; i < C; i += 32) x[static_cast<size_t>(row) * ldx + i] = c[static_cast<size_t>(row) * ldc + i];
+}
+
+// one warp per token row of the conditional half
+__global__ void __launch_bounds__(256) cfg_euler_kernel(float* __restrict__ x, long long ldx, const float* __restrict__ pred,
+                                                        long long ldp, int half_rows, int C, const int* __restrict__ row_pos,
+                                                        const float* __restrict__ dts, int step, float cfg,
+                                                        __nv_bfloat16* __restrict__ xb, long long ldxb, int C_pad) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= half_rows) return;
+  const int lane = threadIdx.x & 31;
+  const bool live = row_pos[row] >= 0;
+  const float dt = dts[step];
+  float* xr = x + static_cast<size_t>(row) * ldx;
+  const float* pc = pred + static_cast<size_t>(row) * ldp;
+  const float* pu = pred + static_cast<size_t>(row + half_rows) * ldp;
+  __nv_bfloat16* b0 = xb + static_cast<size_t>(row) * ldxb;
+  __nv_bfloat16* b1 = xb + static_cast<size_t>(row + half_rows) * ldxb;
+  for (int c = lane * 2; c < C_pad; c += 64) {
+    float v0 = 0.f, v1 = 0.f;
+    if (live && c < C) {
+      const float a = pc[c], u = pu[c];
+      v0 = xr[c] + dt * (a + (a - u) * cfg);
+      xr[c] = v0;
+    }
+    if (live && c + 1 < C) {
+      const float a = pc[c + 1], u = pu[c + 1];
+      v1 = xr[c + 1] + dt * (a + (a - u) * cfg);
+      xr[c + 1] = v1;
+    }
+    const uint32_t w = pack_bf16x2(v0, v1);
+    *reinterpret_cast<uint32_t*>(b0 + c) = w;
+    *reinterpret_cast<uint32_t*>(b1 + c) = w;
+  }
+}
+
+__global__ void time_sinus_kernel(const float* __restrict__ t, int steps, const float* __restrict__ freqs, int dim,
+                                  __nv_bfloat16* __restrict__ out, long long ldo) {
+  const int s = blockIdx.x;
+  const int half = dim / 2;
+  for (int k = threadIdx.x; k < half; k += blockDim.x) {
+    const float arg = (1000.f * t[s]) * freqs[k];
+    out[static_cast<size_t>(s) * ldo + k] = __float2bfloat16(sinf(arg));
+    out[static_cast<size_t>(s) * ldo + half + k] = __float2bfloat16(cosf(arg));
+  }
+}
+
+__global__ void silu_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, long long n) {
+  const long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 2;
+  if (i + 1 < n) {
+    const float2 v = *reinterpret_cast<const float2*>(x + i);
+    *reinterpret_cast<uint32_t*>(y + i) = pack_bf16x2(silu(v.x), silu(v.y));
+  } else if (i < n) {
+    y[i] = __float2bfloat16(silu(x[i]));
+  }
+}
+
+}  // namespace f5
+
+using namespace f5;
+#define F5_STREAM(s) reinterpret_cast<cudaStream_t>(s)
+#define F5_LAUNCH_RC() static_cast<int>(cudaGetLastError())
+
+extern "C" int f5_layernorm_mod(const float* x, int64_t ldx, void* y, int64_t ldy, int32_t M, int32_t D, const float* a,
+                                const float* b, float a_off, float eps, void* stream) {
+  if (!x || !y || !a || !b || M <= 0 || D % 128 != 0 || D > 1024 || ldx % 4 != 0 || ldy % 4 != 0) return F5_ERR_ARG;
+  const int grid = (M + 7) / 8;
+  __nv_bfloat16* yo = reinterpret_cast<__nv_bfloat16*>(y);
+  switch (D / 128) {
+#define F5_CASE(NV) case NV: layernorm_mod_kernel<NV><<<grid, 256, 0, F5_STREAM(stream)>>>(x, ldx, yo, ldy, M, a, b, a_off, eps); break;
+    F5_CASE(1) F5_CASE(2) F5_CASE(3) F5_CASE(4) F5_CASE(5) F5_CASE(6) F5_CASE(7) F5_CASE(8)
+#undef F5_CASE
+  }
+  return F5_LAUNCH_RC();
+}
+
+extern "C" int f5_dwconv7_ln(const float* x, int64_t ldx, void* y, int64_t ldy, int32_t M, int32_t C, const int32_t* row_pos,
+                             const float* w, const float* bias, const float* ln_w, const float* ln_b, float eps,
+                             void* stream) {
+  if (!x || !y || !row_pos || !w || !bias || !ln_w || !ln_b || M <= 0 || C % 128 != 0 || C > 512 || ldx % 4 != 0 || ldy % 4 != 0)
+    return F5_ERR_ARG;
+  const int grid = (M + 7) / 8;
+  __nv_bfloat16* yo = reinterpret_cast<__nv_bfloat16*>(y);
+  switch (C / 128) {
+#define F5_CASE(NV) case NV: dwconv7_ln_kernel<NV><<<grid, 256, 0, F5_STREAM(stream)>>>(x, ldx, yo, ldy, M, row_pos, w, bias, ln_w, ln_b, eps); break;
+    F5_CASE(1) F5_CASE(2) F5_CASE(3) F5_CASE(4)
+#undef F5_CASE
+  }
+  return F5_LAUNCH_RC();
+}
+
+static int max_seg_rows_hint = 4096;  // segments never exceed the reference's 4096-frame clamp (model/cfm.py:93,137)
+
+extern "C" int f5_grn_sumsq(const void* x, int64_t ldx, int32_t C, const int32_t* seg_rows, int32_t num_segs, float* sumsq,
+                            void* stream) {
+  if (!x || !seg_rows || !sumsq || num_segs <= 0 || C % 2 != 0 || ldx % 2 != 0) return F5_ERR_ARG;
+  cudaError_t e = cudaMemsetAsync(sumsq, 0, sizeof(float) * static_cast<size_t>(num_segs) * C, F5_STREAM(stream));
+  if (e != cudaSuccess) return static_cast<int>(e);
+  dim3 grid((max_seg_rows_hint + GRN_ROWS - 1) / GRN_ROWS, num_segs);
+  grn_sumsq_kernel<<<grid, 256, 0, F5_STREAM(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(x), ldx, C, seg_rows, sumsq);
+  return F5_LAUNCH_RC();
+}
+
+extern "C" int f5_grn_apply(void* x, int64_t ldx, int32_t C, const int32_t* seg_rows, int32_t num_segs, const float* sumsq,
+                            const float* gamma, const float* beta, void* stream) {
+  if (!x || !seg_rows || !sumsq || !gamma || !beta || num_segs <= 0 || C % 2 != 0 || ldx % 2 != 0) return F5_ERR_ARG;
+  dim3 grid((max_seg_rows_hint + GRN_ROWS - 1) / GRN_ROWS, num_segs);
+  grn_apply_kernel<<<grid, 256, 0, F5_STREAM(stream)>>>(reinterpret_cast<__nv_bfloat16*>(x), ldx, C, seg_rows, sumsq, gamma, beta);
+  return F5_LAUNCH_RC();
+}
+
+extern "C" int f5_text_gather_pos(const int32_t* ids, const int32_t* row_pos, const float* emb, const float* pos_table,
+                                  int32_t max_pos, float* out, int64_t ldo, int32_t M, int32_t C, void* stream) {
+  if (!ids || !row_pos || !emb || !pos_table || !out || M <= 0 || C % 4 != 0 || ldo % 4 != 0) return F5_ERR_ARG;
+  text_gather_pos_kernel<<<M, 128, 0, F5_STREAM(stream)>>>(ids, row_pos, emb, pos_table, max_pos, out, ldo, M, C);
+  return F5_LAUNCH_RC();
+}
+
+extern "C" int f5_pack_bf16(const float* src, int64_t lds, void* dst, int64_t ldd, int32_t dst_col, int32_t M, int32_t C,
+                            int32_t C_pad, const int32_t* src_rows, const int32_t* row_pos, void* stream) {
+  if (!src || !dst || M <= 0 || C <= 0 || C_pad < C || C_pad % 2 != 0 || dst_col % 2 != 0 || ldd % 2 != 0) return F5_ERR_ARG;
+  pack_bf16_kernel<<<(M + 7) / 8, 256, 0, F5_STREAM(stream)>>>(src, lds, reinterpret_cast<__nv_bfloat16*>(dst), ldd, dst_col,
+                                                               M, C, C_pad, src_rows, row_pos);
+  return F5_LAUNCH_RC();
+}
+
+extern "C" int f5_where_rows(float* x, int64_t ldx, const float* c, int64_t ldc, const int32_t* flag, int32_t M, int32_t C,
+                             void* stream) {
+  if (!x || !c || !flag || M <= 0 || C <= 0) return F5_ERR_ARG;
+  where_rows_kernel<<<(M + 7) / 8, 256, 0, F5_STREAM(stream)>>>(x, ldx, c, ldc, flag, M, C);
+  return F5_LAUNCH_RC();
+}
+
+extern "C" int f5_cfg_euler(float* x, int64_t ldx, const float* pred, int64_t ldp, int32_t half_rows, int32_t C,
+                            const int32_t* row_pos, const float* dts, int32_t step, float cfg_strength, void* xb,
+                            int64_t ldxb, int32_t C_pad, void* stream) {
+  if (!x || !pred || !row_pos || !dts || !xb || half_rows <= 0 || C <= 0 || C_pad < C || C_pad % 2 != 0 || ldxb % 2 != 0)
+    return F5_ERR_ARG;
+  cfg_euler_kernel<<<(half_rows + 7) / 8, 256, 0, F5_STREAM(stream)>>>(x, ldx, pred, ldp, half_rows, C, row_pos, dts, step,
+                                                                       cfg_strength, reinterpret_cast<__nv_bfloat16*>(xb),
+                                                                       ldxb, C_pad);
+  return F5_LAUNCH_RC();
+}
+
+extern "C" int f5_time_sinus(const float* t, int32_t steps, const float* freqs, int32_t dim, void* out, int64_t ldo,
+                             void* stream) {
+  if (!t || !freqs || !out || steps <= 0 || dim <= 0 || dim % 2 != 0) return F5_ERR_ARG;
+  time_sinus_kernel<<<steps, 128, 0, F5_STREAM(stream)>>>(t, steps, freqs, dim, reinterpret_cast<__nv_bfloat16*>(out), ldo);
+  return F5_LAUNCH_RC();
+}
+
+extern "C" int f5_silu_bf16(const float* x, void* out, int64_t n, void* stream) {
+  if (!x || !out || n <= 0) return F5_ERR_ARG;
+  const long long pairs = (n + 1) / 2;
+  silu_bf16_kernel<<<static_cast<unsigned>((pairs + 255) / 256), 256, 0, F5_STREAM(stream)>>>(
+      x, reinterpret_cast<__nv_bfloat16*>(out), n);
+  return F5_LAUNCH_RC();
+}
+
+extern "C" int f5_device_check(void) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return F5_ERR_ARCH;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return F5_ERR_ARCH;
+  return (prop.major == 10 && prop.minor == 0) ? F5_OK : F5_ERR_ARCH;
+}
+
+extern "C" const char* f5_version(void) { return "f5_b200 0.1 (sm_100a; tcgen05/TMEM/TMA)"; }

@@ -1,0 +1,372 @@
+// Persistent warp-specialised tcgen05 GEMM / implicit-conv kernel for sm_100a.
+//
+//   D[M,N] = A[M,K] * B[N,K]^T     bf16 operands (K-major, TMA 128B-swizzled tiles), fp32 accumulators in TMEM.
+//
+//   warp 0    : TMA producer    (one lane; ring of STAGES {A 128x64, B BLOCK_Nx64} tiles, full/empty mbarriers)
+//   warp 1    : MMA issuer      (one lane; tcgen05.mma 128 x BLOCK_N x 16, commits release smem stages / signal epilogue)
+//   warps 2-5 : epilogue        (tcgen05.ld 32 lanes x 32 columns -> registers -> fused epilogue -> global)
+//   TMEM      : 2 accumulator buffers of BLOCK_N fp32 columns, so the epilogue of tile i overlaps the MMAs of tile i+1.
+//
+// Tiles are walked n-fastest so that the CTAs running concurrently share A row-blocks through L2 while B (weights,
+// a few MB) stays L2-resident.
+#include "f5_common.cuh"
+#include "../../include/f5_b200.h"
+
+namespace f5 {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;   // 64 bf16 = 128 B = one swizzle row
+constexpr int UMMA_K = 16;
+constexpr int GEMM_THREADS = 192;
+
+template <int BLOCK_N>
+struct GemmCfg {
+  static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+  static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = BLOCK_N == 256 ? 4 : (BLOCK_N == 128 ? 6 : 8);
+  static constexpr int TMEM_COLS = 2 * BLOCK_N;  // 512 / 256 / 128: powers of two >= 32
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+struct GemmParams {
+  int M, N, num_m_tiles, num_n_tiles, num_k;
+  int kc_per_tap, tap_pad, a_grouped, b_tap_rows;
+  int mode, act;
+  const float* bias;
+  const float* gate;
+  void* out; long long ldo;
+  void* out2; long long ldo2;
+  const float* addend; long long ld_add;
+  float* resid; long long ldr;
+  const int* row_pos; int mask_rows;
+  const float* rope; int rope_period, rope_tiles;
+};
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  switch (act) {
+    case F5_ACT_GELU_TANH: return gelu_tanh(v);
+    case F5_ACT_GELU_ERF: return gelu_erf(v);
+    case F5_ACT_MISH: return mish(v);
+    default: return v;
+  }
+}
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                    const GemmParams p) {
+  using Cfg = GemmCfg<BLOCK_N>;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + Cfg::STAGES;
+  uint64_t* tmem_full = empty_bar + Cfg::STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int i = 0; i < Cfg::STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 128);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / p.num_n_tiles) * BLOCK_M;
+        const int n0 = (tile % p.num_n_tiles) * BLOCK_N;
+        for (int k = 0; k < p.num_k; ++k) {
+          const int tap = k / p.kc_per_tap;
+          const int kc = k - tap * p.kc_per_tap;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+          uint8_t* sb = sa + Cfg::A_BYTES;
+          mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          tma_load_2d(sa, &tmap_a, &full_bar[stage], (p.a_grouped ? n0 : 0) + kc * BLOCK_K, m0 + tap - p.tap_pad);
+          tma_load_2d(sb, &tmap_b, &full_bar[stage], kc * BLOCK_K, tap * p.b_tap_rows + n0);
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M, BLOCK_N);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        for (int k = 0; k < p.num_k; ++k) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint64_t adesc = umma_desc_k_sw128(sa);
+          const uint64_t bdesc = umma_desc_k_sw128(sa + Cfg::A_BYTES);
+#pragma unroll
+          for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk) {
+            // advance 16 bf16 = 32 B along K inside the 128-B swizzle row: +2 in the (addr >> 4) field
+            umma_f16_ss(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, (k | kk) != 0);
+          }
+          umma_commit(&empty_bar[stage]);   // smem stage reusable once these MMAs retire
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full[acc]);       // accumulator ready for the epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue (warps 2..5)
+    const int quarter = warp & 3;           // TMEM lane quarter this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile / p.num_n_tiles) * BLOCK_M;
+      const int n0 = (tile % p.num_n_tiles) * BLOCK_N;
+      const int m = m0 + quarter * 32 + lane;
+      const bool row_ok = m < p.M;
+      int pos = 0;
+      if (p.row_pos != nullptr && row_ok) pos = p.row_pos[m];
+      const bool zero_row = p.mask_rows && pos < 0;
+      const bool rope_tile = p.rope != nullptr && (n0 % p.rope_period) == 0 && (n0 / p.rope_period) < p.rope_tiles;
+
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BLOCK_N + c * 32, r);
+        tmem_ld_wait();
+        const int nc = n0 + c * 32;
+        if (row_ok && nc < p.N) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          if (p.bias != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              if (nc + j < p.N) {
+                const float4 b4 = *reinterpret_cast<const float4*>(p.bias + nc + j);
+                v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+              }
+            }
+          }
+          if (p.act != F5_ACT_NONE) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act);
+          }
+          if (p.mode == F5_EPI_STORE_BF16) {
+            if (rope_tile && c < 2 && pos >= 0) {
+              // interleaved-pair rotation of head 0 (x-transformers apply_rotary_pos_emb; model/modules.py:418-419)
+              const float2* cs = reinterpret_cast<const float2*>(p.rope) + static_cast<size_t>(pos) * 32 + c * 16;
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const float2 t = cs[i];
+                const float x0 = v[2 * i], x1 = v[2 * i + 1];
+                v[2 * i] = x0 * t.x - x1 * t.y;
+                v[2 * i + 1] = x1 * t.x + x0 * t.y;
+              }
+            }
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(m) * p.ldo + nc;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              if (nc + j < p.N) {
+                uint4 q;
+                if (zero_row) {
+                  q = make_uint4(0, 0, 0, 0);
+                } else {
+                  q.x = pack_bf16x2(v[j], v[j + 1]); q.y = pack_bf16x2(v[j + 2], v[j + 3]);
+                  q.z = pack_bf16x2(v[j + 4], v[j + 5]); q.w = pack_bf16x2(v[j + 6], v[j + 7]);
+                }
+                *reinterpret_cast<uint4*>(o + j) = q;
+              }
+            }
+          } else if (p.mode == F5_EPI_STORE_F32) {
+            if (p.addend != nullptr) {
+              const float* a = p.addend + static_cast<size_t>(m) * p.ld_add + nc;
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                if (nc + j < p.N) {
+                  const float4 a4 = *reinterpret_cast<const float4*>(a + j);
+                  v[j] += a4.x; v[j + 1] += a4.y; v[j + 2] += a4.z; v[j + 3] += a4.w;
+                }
+              }
+            }
+            float* o = reinterpret_cast<float*>(p.out) + static_cast<size_t>(m) * p.ldo + nc;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              if (nc + j < p.N) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            }
+            if (p.out2 != nullptr) {
+              __nv_bfloat16* o2 = reinterpret_cast<__nv_bfloat16*>(p.out2) + static_cast<size_t>(m) * p.ldo2 + nc;
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                if (nc + j < p.N) {
+                  uint4 q;
+                  if (zero_row) {
+                    q = make_uint4(0, 0, 0, 0);
+                  } else {
+                    q.x = pack_bf16x2(v[j], v[j + 1]); q.y = pack_bf16x2(v[j + 2], v[j + 3]);
+                    q.z = pack_bf16x2(v[j + 4], v[j + 5]); q.w = pack_bf16x2(v[j + 6], v[j + 7]);
+                  }
+                  *reinterpret_cast<uint4*>(o2 + j) = q;
+                }
+              }
+            }
+          } else {  // F5_EPI_RESID_F32
+            float* x = p.resid + static_cast<size_t>(m) * p.ldr + nc;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              if (nc + j < p.N) {
+                float4 x4 = *reinterpret_cast<const float4*>(x + j);
+                float4 g4 = make_float4(1.f, 1.f, 1.f, 1.f);
+                if (p.gate != nullptr) g4 = *reinterpret_cast<const float4*>(p.gate + nc + j);
+                x4.x += g4.x * v[j]; x4.y += g4.y * v[j + 1]; x4.z += g4.z * v[j + 2]; x4.w += g4.w * v[j + 3];
+                *reinterpret_cast<float4*>(x + j) = x4;
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tmem_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess) {
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+  }
+  return fn;
+}
+
+// 2-D bf16 tensor [rows, cols] with row stride ld (elements); box = {64 cols, box_rows}; 128-B swizzle; OOB -> 0.
+int make_tmap_bf16_2d(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, int box_rows) {
+  EncodeTiledFn enc = get_encode_tiled();
+  if (enc == nullptr) return F5_ERR_DRIVER;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld % 8) != 0 || rows <= 0 || cols <= 0) return F5_ERR_ARG;
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint32_t box[2] = {64, static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? F5_OK : F5_ERR_DRIVER;
+}
+
+template <int BLOCK_N>
+int launch_gemm(const f5_gemm_args& a, const GemmParams& p, cudaStream_t stream) {
+  using Cfg = GemmCfg<BLOCK_N>;
+  CUtensorMap ta, tb;
+  int rc = make_tmap_bf16_2d(&ta, a.A, a.a_rows, a.a_cols, a.lda, BLOCK_M);
+  if (rc != F5_OK) return rc;
+  rc = make_tmap_bf16_2d(&tb, a.B, a.b_rows, a.b_cols, a.ldb, BLOCK_N);
+  if (rc != F5_OK) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    attr_set = true;
+  }
+  const int sms = a.num_sms > 0 ? a.num_sms : kNumSMsB200;
+  const int tiles = p.num_m_tiles * p.num_n_tiles;
+  const int grid = tiles < sms ? tiles : sms;
+  gemm_tcgen05_kernel<BLOCK_N><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, p);
+  return static_cast<int>(cudaGetLastError());
+}
+
+}  // namespace f5
+
+extern "C" int f5_gemm_bf16(const f5_gemm_args* a, void* stream) {
+  using namespace f5;
+  if (a == nullptr || a->A == nullptr || a->B == nullptr) return F5_ERR_ARG;
+  if (a->M <= 0 || a->N <= 0 || (a->N % 8) != 0) return F5_ERR_ARG;
+  if (a->num_taps < 1 || a->kc_per_tap < 1) return F5_ERR_ARG;
+  if (a->block_n != 64 && a->block_n != 128 && a->block_n != 256) return F5_ERR_ARG;
+  if (a->a_grouped && a->block_n != 64) return F5_ERR_ARG;
+  GemmParams p;
+  p.M = a->M; p.N = a->N;
+  p.num_m_tiles = (a->M + BLOCK_M - 1) / BLOCK_M;
+  p.num_n_tiles = (a->N + a->block_n - 1) / a->block_n;
+  p.num_k = a->num_taps * a->kc_per_tap;
+  p.kc_per_tap = a->kc_per_tap; p.tap_pad = a->tap_pad; p.a_grouped = a->a_grouped; p.b_tap_rows = a->b_tap_rows;
+  p.mode = a->mode; p.act = a->act;
+  p.bias = a->bias; p.gate = a->gate;
+  p.out = a->out; p.ldo = a->ldo; p.out2 = a->out2; p.ldo2 = a->ldo2;
+  p.addend = a->addend; p.ld_add = a->ld_add;
+  p.resid = a->resid; p.ldr = a->ldr;
+  p.row_pos = a->row_pos; p.mask_rows = a->mask_rows;
+  p.rope = a->rope; p.rope_period = a->rope_period > 0 ? a->rope_period : 1; p.rope_tiles = a->rope_tiles;
+  switch (a->mode) {
+    case F5_EPI_STORE_BF16:
+      if (a->out == nullptr || (a->ldo % 8) != 0) return F5_ERR_ARG;
+      if (a->rope != nullptr && a->row_pos == nullptr) return F5_ERR_ARG;
+      break;
+    case F5_EPI_STORE_F32:
+      if (a->out == nullptr || (a->ldo % 4) != 0) return F5_ERR_ARG;
+      if (a->out2 != nullptr && (a->ldo2 % 8) != 0) return F5_ERR_ARG;
+      if (a->addend != nullptr && (a->ld_add % 4) != 0) return F5_ERR_ARG;
+      break;
+    case F5_EPI_RESID_F32:
+      if (a->resid == nullptr || (a->ldr % 4) != 0) return F5_ERR_ARG;
+      break;
+    default:
+      return F5_ERR_ARG;
+  }
+  if (a->mask_rows && a->row_pos == nullptr) return F5_ERR_ARG;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (a->block_n == 256) return launch_gemm<256>(*a, p, s);
+  if (a->block_n == 128) return launch_gemm<128>(*a, p, s);
+  return launch_gemm<64>(*a, p, s);
+}
