@@ -76,12 +76,12 @@ int f5_gemm_bf16(const f5_gemm_args* args, void* stream);
  * tiles: int32 [num_tiles, 4] = {q_row0, kv_row0, kv_len, q_rows_valid}.  out: bf16 [rows, ldo], head h at h*64. */
 int f5_attention_d64(const void* qkv, int64_t ld, int32_t rows, int32_t q_col, int32_t k_col, int32_t v_col,
                      int32_t heads, const int32_t* tiles, int32_t num_tiles, void* out, int64_t ldo,
-                     float softmax_scale, int32_t variant, const void* vt, int64_t ld_vt, void* stream);
+                     float softmax_scale, void* stream);
 
-/* y_bf16[m,:] = LayerNorm(x_f32[m,:], eps) * (a_off + a[:]) + b[:]   — model/modules.py:289,:310,:568 (a_off = 1,
+/* y[m,:] = LayerNorm(x_f32[m,:], eps) * (a_off + a[:]) + b[:] (bf16 and/or fp32 output, either may be NULL) — model/modules.py:289,:310,:568 (a_off = 1,
  * a = scale, b = shift) and the affine LayerNorms of ConvNeXtV2 / Vocos (a_off = 0, a = weight, b = bias).  D % 128 == 0, D <= 1024. */
-int f5_layernorm_mod(const float* x, int64_t ldx, void* y, int64_t ldy, int32_t M, int32_t D, const float* a,
-                     const float* b, float a_off, float eps, void* stream);
+int f5_layernorm_mod(const float* x, int64_t ldx, void* y_bf16, int64_t ldy, float* y_f32, int64_t ldy32, int32_t M,
+                     int32_t D, const float* a, const float* b, float a_off, float eps, void* stream);
 
 /* Depthwise Conv1d(k=7, pad=3) over the rows of one utterance + affine LayerNorm -> bf16
  * (model/modules.py:262-264; Vocos ConvNeXtBlock).  row_pos marks utterance membership (halo rows with row_pos < 0 or

@@ -51,8 +51,8 @@ def _load() -> C.CDLL:
     vp, i32, i64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
     sig = {
         "f5_gemm_bf16": [C.POINTER(GemmArgs), vp],
-        "f5_attention_d64": [vp, i64, i32, i32, i32, i32, i32, vp, i32, vp, i64, f32, i32, vp, i64, vp],
-        "f5_layernorm_mod": [vp, i64, vp, i64, i32, i32, vp, vp, f32, f32, vp],
+        "f5_attention_d64": [vp, i64, i32, i32, i32, i32, i32, vp, i32, vp, i64, f32, vp],
+        "f5_layernorm_mod": [vp, i64, vp, i64, vp, i64, i32, i32, vp, vp, f32, f32, vp],
         "f5_dwconv7_ln": [vp, i64, vp, i64, i32, i32, vp, vp, vp, vp, vp, f32, vp],
         "f5_grn_sumsq": [vp, i64, i32, vp, i32, vp, vp],
         "f5_grn_apply": [vp, i64, i32, vp, i32, vp, vp, vp, vp],

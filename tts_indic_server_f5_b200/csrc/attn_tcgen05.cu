@@ -8,8 +8,7 @@
 //               P_j written as bf16 into a 128B-swizzled K-major smem tile, O rescaled in TMEM when the running max moved.
 // Two CTAs fit per SM (112 KB smem, 256 TMEM columns each) so one CTA's softmax overlaps the other's MMAs.
 //
-// V operand: variant 0 reads V tiles [keys, d] straight from the qkv buffer and feeds them as an MN-major B operand;
-//            variant 1 reads a pre-transposed V^T [d, tokens] as a K-major B operand (validation fallback).
+// V tiles [keys, d] are read straight from the qkv buffer and fed to the PV MMA as an MN-major B operand (no transpose pass).
 #include "f5_common.cuh"
 #include "../../include/f5_b200.h"
 
@@ -29,7 +28,6 @@ struct AttnParams {
   __nv_bfloat16* out;
   long long ldo;
   float scale_log2;
-  int variant;
 };
 
 __device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_t (&r)[32]) {
@@ -57,8 +55,7 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr) {
 }
 
 __global__ void __launch_bounds__(ATT_THREADS, 2)
-attn_d64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_vt,
-                const AttnParams p) {
+attn_d64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();   // 128B-swizzled tiles need 1024-B aligned bases
   uint8_t* sQ = smem;
@@ -83,7 +80,6 @@ attn_d64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_qkv);
-    if (p.variant == 1) tma_prefetch_desc(&tmap_vt);
     mbar_init(q_full, 1);
     mbar_init(&kv_full[0], 1); mbar_init(&kv_full[1], 1);
     mbar_init(&kv_empty[0], 1); mbar_init(&kv_empty[1], 1);
@@ -112,19 +108,13 @@ attn_d64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
         mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1);
         mbar_expect_tx(&kv_full[st], 2 * ATT_TILE_BYTES);
         tma_load_2d(sK + st * ATT_TILE_BYTES, &tmap_qkv, &kv_full[st], p.k_col + head * ATT_D, kv_row0 + j * ATT_BN);
-        if (p.variant == 0) {
-          tma_load_2d(sV + st * ATT_TILE_BYTES, &tmap_qkv, &kv_full[st], p.v_col + head * ATT_D, kv_row0 + j * ATT_BN);
-        } else {
-          tma_load_2d(sV + st * ATT_TILE_BYTES, &tmap_vt, &kv_full[st], kv_row0 + j * ATT_BN, head * ATT_D);
-          tma_load_2d(sV + st * ATT_TILE_BYTES + ATT_TILE_BYTES / 2, &tmap_vt, &kv_full[st], kv_row0 + j * ATT_BN + 64,
-                      head * ATT_D);
-        }
+        tma_load_2d(sV + st * ATT_TILE_BYTES, &tmap_qkv, &kv_full[st], p.v_col + head * ATT_D, kv_row0 + j * ATT_BN);
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc_qk = umma_idesc_bf16(ATT_BM, ATT_BN);
-      const uint32_t idesc_pv = umma_idesc_bf16(ATT_BM, ATT_D) | (p.variant == 0 ? (1u << 16) : 0u);
+      constexpr uint32_t idesc_pv = umma_idesc_bf16(ATT_BM, ATT_D) | (1u << 16);   // B (= V) is MN-major
       const uint64_t qdesc = umma_desc_k_sw128(smem_u32(sQ));
       mbar_wait(q_full, 0);
       mbar_wait(&kv_full[0], 0);
@@ -153,10 +143,7 @@ attn_d64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
 #pragma unroll
         for (int kk = 0; kk < ATT_BN / 16; ++kk) {
           const uint64_t pdesc = umma_desc_k_sw128(sp + (kk >> 2) * ATT_TILE_BYTES) + 2 * (kk & 3);
-          uint64_t vdesc;
-          if (p.variant == 0) vdesc = umma_desc_mn_sw128(sv + kk * 2048);
-          else vdesc = umma_desc_k_sw128(sv + (kk >> 2) * (ATT_TILE_BYTES / 2)) + 2 * (kk & 3);
-          umma_f16_ss(tmem_O, pdesc, vdesc, idesc_pv, (j | kk) != 0);
+          umma_f16_ss(tmem_O, pdesc, umma_desc_mn_sw128(sv + kk * 2048), idesc_pv, (j | kk) != 0);   // 16 keys = 2 KB
         }
         umma_commit(&kv_empty[st]);
         umma_commit(o_full);
@@ -271,20 +258,14 @@ int make_tmap_bf16_2d(CUtensorMap* map, const void* base, long long rows, long l
 
 extern "C" int f5_attention_d64(const void* qkv, int64_t ld, int32_t rows, int32_t q_col, int32_t k_col, int32_t v_col,
                                 int32_t heads, const int32_t* tiles, int32_t num_tiles, void* out, int64_t ldo,
-                                float softmax_scale, int32_t variant, const void* vt, int64_t ld_vt, void* stream) {
+                                float softmax_scale, void* stream) {
   using namespace f5;
   if (qkv == nullptr || tiles == nullptr || out == nullptr || num_tiles <= 0 || heads <= 0) return F5_ERR_ARG;
-  if ((ldo % 8) != 0 || (variant != 0 && variant != 1) || (variant == 1 && vt == nullptr)) return F5_ERR_ARG;
+  if ((ldo % 8) != 0) return F5_ERR_ARG;
   const int cols = (q_col > k_col ? (q_col > v_col ? q_col : v_col) : (k_col > v_col ? k_col : v_col)) + heads * ATT_D;
-  CUtensorMap tq, tv;
+  CUtensorMap tq;
   int rc = make_tmap_bf16_2d(&tq, qkv, rows, cols, ld, 128);
   if (rc != F5_OK) return rc;
-  if (variant == 1) {
-    rc = make_tmap_bf16_2d(&tv, vt, heads * ATT_D, rows, ld_vt, 64);
-    if (rc != F5_OK) return rc;
-  } else {
-    tv = tq;
-  }
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(attn_d64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM);
@@ -297,8 +278,7 @@ extern "C" int f5_attention_d64(const void* qkv, int64_t ld, int32_t rows, int32
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
   p.ldo = ldo;
   p.scale_log2 = softmax_scale * 1.4426950408889634f;
-  p.variant = variant;
   dim3 grid(num_tiles, heads);
-  attn_d64_kernel<<<grid, ATT_THREADS, ATT_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(tq, tv, p);
+  attn_d64_kernel<<<grid, ATT_THREADS, ATT_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(tq, p);
   return static_cast<int>(cudaGetLastError());
 }

@@ -9,7 +9,8 @@ namespace f5 {
 // ------------------------------------------------------------------------------------------------ LayerNorm * a + b -> bf16
 template <int NV>  // float4 per lane: D = NV * 128
 __global__ void __launch_bounds__(256) layernorm_mod_kernel(const float* __restrict__ x, long long ldx,
-                                                            __nv_bfloat16* __restrict__ y, long long ldy, int M,
+                                                            __nv_bfloat16* __restrict__ y, long long ldy,
+                                                            float* __restrict__ y32, long long ldy32, int M,
                                                             const float* __restrict__ a, const float* __restrict__ b,
                                                             float a_off, float eps) {
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -41,7 +42,9 @@ __global__ void __launch_bounds__(256) layernorm_mod_kernel(const float* __restr
     const float o1 = (v[i].y - mean) * rstd * (a_off + a4.y) + b4.y;
     const float o2 = (v[i].z - mean) * rstd * (a_off + a4.z) + b4.z;
     const float o3 = (v[i].w - mean) * rstd * (a_off + a4.w) + b4.w;
-    yr[i * 32 + lane] = make_uint2(pack_bf16x2(o0, o1), pack_bf16x2(o2, o3));
+    if (y != nullptr) yr[i * 32 + lane] = make_uint2(pack_bf16x2(o0, o1), pack_bf16x2(o2, o3));
+    if (y32 != nullptr)
+      reinterpret_cast<float4*>(y32 + static_cast<size_t>(row) * ldy32)[i * 32 + lane] = make_float4(o0, o1, o2, o3);
   }
 }
 
@@ -70,7 +73,8 @@ __global__ void __launch_bounds__(256) dwconv7_ln_kernel(const float* __restrict
   for (int k = 0; k < 7; ++k) {
     const int rr = row + k - 3;
     if (rr < 0 || rr >= M) continue;
-    if (row_pos[rr] != pos + k - 3) continue;  // neighbour belongs to another utterance / gap => zero padding
+    const int pr = row_pos[rr];
+    if (pr < 0 || pr != pos + k - 3) continue;  // gap row or another utterance => zero padding
     const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(rr) * ldx);
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
@@ -266,13 +270,14 @@ using namespace f5;
 #define F5_STREAM(s) reinterpret_cast<cudaStream_t>(s)
 #define F5_LAUNCH_RC() static_cast<int>(cudaGetLastError())
 
-extern "C" int f5_layernorm_mod(const float* x, int64_t ldx, void* y, int64_t ldy, int32_t M, int32_t D, const float* a,
-                                const float* b, float a_off, float eps, void* stream) {
-  if (!x || !y || !a || !b || M <= 0 || D % 128 != 0 || D > 1024 || ldx % 4 != 0 || ldy % 4 != 0) return F5_ERR_ARG;
+extern "C" int f5_layernorm_mod(const float* x, int64_t ldx, void* y, int64_t ldy, float* y32, int64_t ldy32, int32_t M,
+                                int32_t D, const float* a, const float* b, float a_off, float eps, void* stream) {
+  if (!x || (!y && !y32) || !a || !b || M <= 0 || D % 128 != 0 || D > 1024 || ldx % 4 != 0 || ldy % 4 != 0 || ldy32 % 4 != 0)
+    return F5_ERR_ARG;
   const int grid = (M + 7) / 8;
   __nv_bfloat16* yo = reinterpret_cast<__nv_bfloat16*>(y);
   switch (D / 128) {
-#define F5_CASE(NV) case NV: layernorm_mod_kernel<NV><<<grid, 256, 0, F5_STREAM(stream)>>>(x, ldx, yo, ldy, M, a, b, a_off, eps); break;
+#define F5_CASE(NV) case NV: layernorm_mod_kernel<NV><<<grid, 256, 0, F5_STREAM(stream)>>>(x, ldx, yo, ldy, y32, ldy32, M, a, b, a_off, eps); break;
     F5_CASE(1) F5_CASE(2) F5_CASE(3) F5_CASE(4) F5_CASE(5) F5_CASE(6) F5_CASE(7) F5_CASE(8)
 #undef F5_CASE
   }

@@ -1,0 +1,348 @@
+"""B200-native CFM sampler + DiT backbone (the hot path of `CFM.sample`, reference `f5_tts/model/cfm.py:81-210`
+and `f5_tts/model/backbones/dit.py:130-163`).
+
+Design (B200-first, not a port):
+  * all utterances of a batch are packed into one row matrix (layout.py); the conditional and unconditional CFG
+    branches are the two halves of the SAME matrix, so every GEMM / attention launch covers the whole batch once;
+  * everything that does not depend on the ODE state is hoisted out of the 32-step loop: the time embedding and ALL
+    AdaLN modulation vectors for all steps and layers are one GEMM (t is a scalar shared by the batch,
+    dit.py:141-142); the text embedding (ConvNeXtV2 stack, both CFG variants) and the step-invariant part of the
+    input projection `W_c cond + W_t text + b` are computed once per batch; per step only `W_x x` (K=100) is new;
+  * the residual stream, LayerNorm statistics, softmax, ODE state and time grid stay fp32; bf16 appears only as
+    tensor-core operands;
+  * the step loop (32 x (3 + 7*depth + 3) launches) is captured once per layout shape in a CUDA graph.
+Every arithmetic op is a launcher of `libf5b200.so` (ops.py); torch provides device memory and streams only.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+
+import torch
+
+from . import ops
+from .layout import PackedLayout, build_layout
+from .weights import DiTConfig
+
+BF16, F32, I32 = torch.bfloat16, torch.float32, torch.int32
+MELP = 128  # mel channels padded to one 128-B bf16 swizzle row pair (K = 128)
+
+
+def sway_time_grid(steps: int, sway_sampling_coef: float | None) -> torch.Tensor:
+    """cfm.py:196-198 in fp32 (the fp32 grid is exact to 1 ulp; a bf16 grid would duplicate a point)."""
+    t = torch.linspace(0, 1, steps + 1, dtype=torch.float32)
+    if sway_sampling_coef is not None:
+        t = t + sway_sampling_coef * (torch.cos(torch.pi / 2 * t) - 1 + t)
+    return t
+
+
+def _conv_pos_weight(w: torch.Tensor) -> torch.Tensor:
+    """[D, cpg, K] grouped-conv weight -> [K*D, 64] per-tap K-major tiles of 64 input channels.  Groups narrower than
+    64 channels are merged block-diagonally into 64-wide super-groups (exact; only tiny test configs need it)."""
+    D, cpg, K = w.shape
+    if cpg == 64:
+        return w.permute(2, 0, 1).reshape(K * D, 64).contiguous()
+    assert 64 % cpg == 0 and D % 64 == 0, "conv_pos group width must divide 64"
+    wt = torch.zeros(K, D, 64, dtype=w.dtype)
+    o = torch.arange(D)
+    off = ((o // cpg) % (64 // cpg)) * cpg
+    for j in range(cpg):
+        wt[:, o, off + j] = w[:, j, :].t()
+    return wt.reshape(K * D, 64).contiguous()
+
+
+class DiTWeights:
+    """Device-resident weights in the layout the kernels consume (bf16 K-major GEMM operands, fp32 vectors)."""
+
+    def __init__(self, sd: dict, cfg: DiTConfig, device):
+        self.cfg = cfg
+        p = "transformer."
+        D, TD, mel, L = cfg.dim, cfg.text_dim, cfg.mel_dim, cfg.depth
+        assert D % 256 == 0 and cfg.dim_head == 64 and cfg.heads * 64 == D and TD % 128 == 0 and mel <= MELP
+
+        def bf(t):
+            return t.to(device=device, dtype=BF16).contiguous()
+
+        def f32(t):
+            return t.to(device=device, dtype=F32).contiguous()
+
+        g = lambda k: sd[p + k].float()  # noqa: E731
+        self.t0_w, self.t0_b = bf(g("time_embed.time_mlp.0.weight")), f32(g("time_embed.time_mlp.0.bias"))
+        self.t2_w, self.t2_b = bf(g("time_embed.time_mlp.2.weight")), f32(g("time_embed.time_mlp.2.bias"))
+        half = cfg.freq_embed_dim // 2
+        self.t_freqs = f32(torch.exp(torch.arange(half).float() * -(math.log(10000) / (half - 1))))  # modules.py:157-158
+        mod_w = [g(f"transformer_blocks.{l}.attn_norm.linear.weight") for l in range(L)] + [g("norm_out.linear.weight")]
+        mod_b = [g(f"transformer_blocks.{l}.attn_norm.linear.bias") for l in range(L)] + [g("norm_out.linear.bias")]
+        self.mod_w, self.mod_b = bf(torch.cat(mod_w)), f32(torch.cat(mod_b))
+        # text embedding
+        self.emb = f32(g("text_embed.text_embed.weight"))
+        freqs = 1.0 / (10000.0 ** (torch.arange(0, TD, 2)[: TD // 2].float() / TD))          # modules.py:196-207
+        ang = torch.outer(torch.arange(cfg.max_pos), freqs).float()
+        self.pos_table = f32(torch.cat([torch.cos(ang), torch.sin(ang)], dim=-1))
+        self.text_blocks = []
+        for i in range(cfg.conv_layers):
+            b = f"text_embed.text_blocks.{i}."
+            self.text_blocks.append(dict(
+                dw_w=f32(g(b + "dwconv.weight").reshape(TD, 7)), dw_b=f32(g(b + "dwconv.bias")),
+                ln_w=f32(g(b + "norm.weight")), ln_b=f32(g(b + "norm.bias")),
+                pw1_w=bf(g(b + "pwconv1.weight")), pw1_b=f32(g(b + "pwconv1.bias")),
+                grn_g=f32(g(b + "grn.gamma").reshape(-1)), grn_b=f32(g(b + "grn.beta").reshape(-1)),
+                pw2_w=bf(g(b + "pwconv2.weight")), pw2_b=f32(g(b + "pwconv2.bias"))))
+        # input projection split by source (dit.py:85): [x | cond | text]
+        W = g("input_embed.proj.weight")
+        wx = torch.zeros(D, MELP)
+        wx[:, :mel] = W[:, :mel]
+        wc = torch.zeros(D, MELP)
+        wc[:, :mel] = W[:, mel:2 * mel]
+        self.wx = bf(wx)
+        self.wct = bf(torch.cat([wc, W[:, 2 * mel:]], dim=1))
+        self.proj_b = f32(g("input_embed.proj.bias"))
+        self.conv_k = cfg.conv_pos_kernel
+        self.c1_w = bf(_conv_pos_weight(g("input_embed.conv_pos_embed.conv1d.0.weight")))
+        self.c1_b = f32(g("input_embed.conv_pos_embed.conv1d.0.bias"))
+        self.c2_w = bf(_conv_pos_weight(g("input_embed.conv_pos_embed.conv1d.2.weight")))
+        self.c2_b = f32(g("input_embed.conv_pos_embed.conv1d.2.bias"))
+        self.blocks = []
+        for l in range(L):
+            b = f"transformer_blocks.{l}."
+            self.blocks.append(dict(
+                qkv_w=bf(torch.cat([g(b + "attn.to_q.weight"), g(b + "attn.to_k.weight"), g(b + "attn.to_v.weight")])),
+                qkv_b=f32(torch.cat([g(b + "attn.to_q.bias"), g(b + "attn.to_k.bias"), g(b + "attn.to_v.bias")])),
+                o_w=bf(g(b + "attn.to_out.0.weight")), o_b=f32(g(b + "attn.to_out.0.bias")),
+                f1_w=bf(g(b + "ff.ff.0.0.weight")), f1_b=f32(g(b + "ff.ff.0.0.bias")),
+                f2_w=bf(g(b + "ff.ff.2.weight")), f2_b=f32(g(b + "ff.ff.2.bias"))))
+        po = torch.zeros(MELP, D)
+        po[:mel] = g("proj_out.weight")
+        pb = torch.zeros(MELP)
+        pb[:mel] = g("proj_out.bias")
+        self.out_w, self.out_b = bf(po), f32(pb)
+        inv = 1.0 / (10000.0 ** (torch.arange(0, 64, 2).float() / 64))                        # x-transformers RotaryEmbedding
+        ra = torch.arange(cfg.max_pos).float()[:, None] * inv[None]
+        self.rope = f32(torch.stack((ra.cos(), ra.sin()), dim=-1).reshape(cfg.max_pos, 64))
+
+
+@dataclass
+class UtteranceInput:
+    """One utterance after the `CFM.sample` prologue (cfm.py:100-149)."""
+    cond: torch.Tensor        # fp32 [F, mel] prompt mel (CPU or CUDA)
+    text_ids: torch.Tensor    # int64 [nt], vocabulary ids (no padding)
+    n: int                    # total frames (duration after the max/clamp rules)
+    cond_len: int             # frames where cond_mask is true (lens after max with text_lens)
+    y0: torch.Tensor          # fp32 [n, mel] initial noise
+    edit_mask: torch.Tensor | None = None   # bool [>= cond_len]
+
+
+class Workspace:
+    """Device buffers for one packed layout size; reused across batches of the same size."""
+
+    def __init__(self, cfg: DiTConfig, R: int, steps_pad: int, device):
+        D, TD, TI, FF, L = cfg.dim, cfg.text_dim, cfg.text_inner, cfg.ff_inner, cfg.depth
+        z = lambda r, c, dt: torch.zeros(r, c, device=device, dtype=dt)  # noqa: E731
+        self.R = R
+        self.x = z(R, MELP, F32)               # ODE state
+        self.cond = z(R, MELP, F32)            # step_cond
+        self.xb = z(2 * R, MELP, BF16)         # bf16 copy of x for both CFG halves
+        self.pred = z(2 * R, MELP, F32)
+        self.xres = z(2 * R, D, F32)           # residual stream
+        self.inv = z(2 * R, D, F32)            # W_c cond + W_t text + b
+        self.hb = z(2 * R, D, BF16)
+        self.ab = z(2 * R, D, BF16)            # conv-1 output / attention output
+        self.qkv = z(2 * R, 3 * D, BF16)
+        self.fb = z(2 * R, FF, BF16)
+        self.te = z(2 * R, TD, F32)
+        self.tb = z(2 * R, TD, BF16)
+        self.gb = z(2 * R, TI, BF16)
+        self.act = z(2 * R, MELP + TD, BF16)
+        self.ids = torch.zeros(2 * R, device=device, dtype=I32)
+        self.row_pos = torch.full((2 * R,), -1, device=device, dtype=I32)
+        self.cond_flag = torch.zeros(R, device=device, dtype=I32)
+        self.tsin = z(steps_pad, cfg.freq_embed_dim, BF16)
+        self.th = z(steps_pad, D, F32)
+        self.thb = z(steps_pad, D, BF16)
+        self.mod = z(steps_pad, (6 * L + 2) * D, F32)
+        self.tgrid = torch.zeros(steps_pad + 1, device=device, dtype=F32)
+        self.dts = torch.zeros(steps_pad, device=device, dtype=F32)
+
+
+class F5Engine:
+    """CUDA sampler for one set of DiT weights.  `sample_packed` is the device-resident hot path."""
+
+    def __init__(self, sd: dict, cfg: DiTConfig, device="cuda", use_graphs: bool = True):
+        from ._lib import lib
+        if not torch.cuda.is_available():
+            raise RuntimeError("F5Engine needs a CUDA device (sm_100a); there is no CPU fallback")
+        torch.cuda.set_device(torch.device(device))
+        rc = lib.f5_device_check()
+        if rc != 0:
+            raise RuntimeError("libf5b200.so targets sm_100a (B200) only")
+        self.cfg, self.device = cfg, torch.device(device)
+        self.w = DiTWeights(sd, cfg, self.device)
+        self.use_graphs = use_graphs
+        self._ws: dict[int, Workspace] = {}
+        self._graphs: dict[tuple, torch.cuda.CUDAGraph] = {}
+        self._tables: dict[tuple, tuple] = {}
+
+    # ------------------------------------------------------------------------------------------ batch set-up
+    def workspace(self, R: int) -> Workspace:
+        ws = self._ws.get(R)
+        if ws is None:
+            ws = self._ws[R] = Workspace(self.cfg, R, 128, self.device)
+        return ws
+
+    def upload(self, utts: list[UtteranceInput], layout: PackedLayout, steps: int, sway: float | None) -> Workspace:
+        """Stage the per-batch inputs in pinned host memory and copy them to the device (H2D on the current stream)."""
+        cfg, R = self.cfg, layout.half_rows
+        ws = self.workspace(R)
+        mel = cfg.mel_dim
+        pin = lambda *s, dt=F32: torch.zeros(*s, dtype=dt).pin_memory()  # noqa: E731
+        h_x, h_cond = pin(R, MELP), pin(R, MELP)
+        h_ids, h_flag = pin(2 * R, dt=I32), pin(R, dt=I32)
+        dev_conds = []
+        for u, s in zip(utts, layout.starts):
+            n = u.n
+            h_x[s:s + n, :mel] = u.y0[:n].float().cpu()
+            F_ = min(u.cond.shape[0], n)
+            mask = torch.zeros(n, dtype=torch.bool)
+            mask[: min(u.cond_len, n)] = True
+            if u.edit_mask is not None:
+                em = u.edit_mask.cpu().bool()[:n]
+                mask[: em.numel()] &= em
+            h_flag[s:s + n] = mask.to(I32)
+            if u.cond.is_cuda and u.edit_mask is None:
+                dev_conds.append((s, min(F_, u.cond_len), u.cond))       # prompt mel already on the device: no host round trip
+            else:
+                c = torch.zeros(n, mel)
+                c[:F_] = u.cond[:F_].float().cpu()
+                h_cond[s:s + n, :mel] = torch.where(mask[:, None], c, torch.zeros_like(c))
+            nt = min(u.text_ids.numel(), n)                      # dit.py:48-51: +1, truncate to n, filler 0
+            h_ids[s:s + nt] = (u.text_ids[:nt] + 1).to(I32)
+        ws.x.copy_(h_x, non_blocking=True)
+        ws.cond.copy_(h_cond, non_blocking=True)
+        for s, f, c in dev_conds:
+            ws.cond[s:s + f, :mel].copy_(c[:f])
+        ws.ids.copy_(h_ids, non_blocking=True)
+        ws.cond_flag.copy_(h_flag, non_blocking=True)
+        ws.row_pos.copy_(layout.row_pos.pin_memory(), non_blocking=True)
+        key = layout.signature()
+        tabs = self._tables.get(key)
+        if tabs is None:
+            tabs = (layout.attn_tiles.to(self.device), layout.seg_rows.to(self.device))
+            self._tables = {key: tabs}          # keep only the latest (tables are tiny; avoids unbounded growth)
+        ws.tiles, ws.segs = tabs
+        ws.sumsq = torch.zeros(ws.segs.shape[0], cfg.text_inner, device=self.device, dtype=F32)
+        t = sway_time_grid(steps, sway)
+        h_t = pin(ws.tgrid.shape[0])
+        h_t[: steps + 1] = t
+        h_dt = pin(ws.dts.shape[0])
+        h_dt[:steps] = t[1:] - t[:-1]                          # torchdiffeq Euler: dt = t1 - t0 in the grid dtype
+        ws.tgrid.copy_(h_t, non_blocking=True)
+        ws.dts.copy_(h_dt, non_blocking=True)
+        ws.h2d_bytes = sum(v.numel() * v.element_size() for v in (h_x, h_cond, h_ids, h_flag, h_t, h_dt)) + \
+            layout.row_pos.numel() * 4
+        return ws
+
+    # ------------------------------------------------------------------------------------------ hoisted work
+    def hoist(self, ws: Workspace, steps: int) -> None:
+        """Step-invariant work: time/AdaLN vectors for all steps, text embedding (both CFG variants), W_c cond + W_t text + b."""
+        cfg, w, R = self.cfg, self.w, ws.R
+        D, TD = cfg.dim, cfg.text_dim
+        # --- time embedding + all modulation vectors (modules.py:648-658, :286, :307)
+        ops.time_sinus(ws.tgrid[:128], w.t_freqs, ws.tsin)
+        ops.gemm(ws.tsin, w.t0_w, mode=ops.F5_EPI_STORE_F32, bias=w.t0_b, out=ws.th)
+        ops.silu_bf16(ws.th, ws.thb)
+        ops.gemm(ws.thb, w.t2_w, mode=ops.F5_EPI_STORE_F32, bias=w.t2_b, out=ws.th)
+        ops.silu_bf16(ws.th, ws.thb)
+        ops.gemm(ws.thb, w.mod_w, mode=ops.F5_EPI_STORE_F32, bias=w.mod_b, out=ws.mod)
+        # --- text embedding, conditional half = real tokens, unconditional half = all filler (dit.py:47-69)
+        ops.text_gather_pos(ws.ids, ws.row_pos, w.emb, w.pos_table, ws.te)
+        for blk in w.text_blocks:                                            # ConvNeXtV2Block, modules.py:259-269
+            ops.dwconv7_ln(ws.te, ws.tb, ws.row_pos, blk["dw_w"], blk["dw_b"], blk["ln_w"], blk["ln_b"])
+            ops.gemm(ws.tb, blk["pw1_w"], mode=ops.F5_EPI_STORE_BF16, act=ops.F5_ACT_GELU_ERF, bias=blk["pw1_b"], out=ws.gb)
+            ops.grn(ws.gb, ws.segs, ws.sumsq, blk["grn_g"], blk["grn_b"])
+            ops.gemm(ws.gb, blk["pw2_w"], mode=ops.F5_EPI_RESID_F32, bias=blk["pw2_b"], resid=ws.te)
+        # --- A = [cond | text] (cond is zero in the unconditional half: drop_audio_cond, dit.py:82-83)
+        ops.pack_bf16(ws.cond, ws.act, 0, cfg.mel_dim, MELP, M=R)
+        ops.pack_bf16(ws.te, ws.act, MELP, TD, TD, row_pos=ws.row_pos)
+        ops.gemm(ws.act, w.wct, mode=ops.F5_EPI_STORE_F32, bias=w.proj_b, out=ws.inv)
+        # --- bf16 copy of the initial state for both halves
+        ops.pack_bf16(ws.x, ws.xb, 0, cfg.mel_dim, MELP, row_pos=ws.row_pos, M=R)
+        ops.pack_bf16(ws.x, ws.xb[R:], 0, cfg.mel_dim, MELP, row_pos=ws.row_pos, M=R)
+
+    # ------------------------------------------------------------------------------------------ one Euler step
+    def step(self, ws: Workspace, s: int, cfg_strength: float) -> None:
+        cfg, w, R = self.cfg, self.w, ws.R
+        D, L, H = cfg.dim, cfg.depth, cfg.heads
+        mod = ws.mod[s]
+        # input embedding: W_x x + (W_c cond + W_t text + b); conv position embedding + residual (dit.py:85-86)
+        ops.gemm(ws.xb, w.wx, mode=ops.F5_EPI_STORE_F32, out=ws.xres, addend=ws.inv, out2=ws.hb, row_pos=ws.row_pos,
+                 mask_rows=True)
+        ops.gemm(ws.hb, w.c1_w, M=2 * R, N=D, mode=ops.F5_EPI_STORE_BF16, act=ops.F5_ACT_MISH, bias=w.c1_b, out=ws.ab,
+                 row_pos=ws.row_pos, mask_rows=True, block_n=64, num_taps=w.conv_k, kc_per_tap=1, tap_pad=w.conv_k // 2,
+                 a_grouped=True, b_tap_rows=D)
+        ops.gemm(ws.ab, w.c2_w, M=2 * R, N=D, mode=ops.F5_EPI_RESID_F32, act=ops.F5_ACT_MISH, bias=w.c2_b, resid=ws.xres,
+                 block_n=64, num_taps=w.conv_k, kc_per_tap=1, tap_pad=w.conv_k // 2, a_grouped=True, b_tap_rows=D)
+        for l, blk in enumerate(w.blocks):                                   # DiTBlock, modules.py:558-572
+            m = mod[l * 6 * D:(l + 1) * 6 * D]
+            shift_msa, scale_msa, gate_msa = m[0:D], m[D:2 * D], m[2 * D:3 * D]
+            shift_mlp, scale_mlp, gate_mlp = m[3 * D:4 * D], m[4 * D:5 * D], m[5 * D:6 * D]
+            ops.layernorm_mod(ws.xres, ws.hb, scale_msa, shift_msa, 1.0)
+            ops.gemm(ws.hb, blk["qkv_w"], mode=ops.F5_EPI_STORE_BF16, bias=blk["qkv_b"], out=ws.qkv, row_pos=ws.row_pos,
+                     rope=w.rope, rope_period=D, rope_tiles=2)
+            ops.attention(ws.qkv, ws.tiles, ws.ab, H, 0, D, 2 * D, 0.125)
+            ops.gemm(ws.ab, blk["o_w"], mode=ops.F5_EPI_RESID_F32, bias=blk["o_b"], gate=gate_msa, resid=ws.xres)
+            ops.layernorm_mod(ws.xres, ws.hb, scale_mlp, shift_mlp, 1.0)
+            ops.gemm(ws.hb, blk["f1_w"], mode=ops.F5_EPI_STORE_BF16, act=ops.F5_ACT_GELU_TANH, bias=blk["f1_b"], out=ws.fb)
+            ops.gemm(ws.fb, blk["f2_w"], mode=ops.F5_EPI_RESID_F32, bias=blk["f2_b"], gate=gate_mlp, resid=ws.xres)
+        mf = mod[6 * L * D:]
+        ops.layernorm_mod(ws.xres, ws.hb, mf[0:D], mf[D:2 * D], 1.0)          # AdaLayerNormZero_Final: (scale, shift)
+        ops.gemm(ws.hb, w.out_w, mode=ops.F5_EPI_STORE_F32, bias=w.out_b, out=ws.pred)
+        ops.cfg_euler(ws.x, ws.pred, R, cfg.mel_dim, ws.row_pos, ws.dts, s, cfg_strength, ws.xb, MELP)
+
+    def run_steps(self, ws: Workspace, steps: int, cfg_strength: float) -> None:
+        key = (ws.R, ws.tiles.shape[0], ws.segs.shape[0], steps, float(cfg_strength), ws.tiles.data_ptr())
+        if not self.use_graphs:
+            for s in range(steps):
+                self.step(ws, s, cfg_strength)
+            return
+        g = self._graphs.get(key)
+        if g is None:
+            x_saved = ws.x.clone()
+            self.step(ws, 0, cfg_strength)            # eager warm-up of every kernel variant (sets func attributes) ...
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):                 # capture records, it does not execute
+                for s in range(steps):
+                    self.step(ws, s, cfg_strength)
+            ws.x.copy_(x_saved)                       # ... then restore the state the warm-up step advanced
+            ops.pack_bf16(ws.x, ws.xb, 0, self.cfg.mel_dim, MELP, row_pos=ws.row_pos, M=ws.R)
+            ops.pack_bf16(ws.x, ws.xb[ws.R:], 0, self.cfg.mel_dim, MELP, row_pos=ws.row_pos, M=ws.R)
+            self._graphs = {key: g}                   # one live graph (its node arguments point into this workspace)
+        g.replay()
+
+    # ------------------------------------------------------------------------------------------ public
+    def sample_packed(self, utts: list[UtteranceInput], steps: int = 32, cfg_strength: float = 2.0,
+                      sway_sampling_coef: float | None = -1.0) -> tuple[Workspace, PackedLayout]:
+        """Run the sampler for a batch; the result stays on the device in `ws.x` (rows per `layout`)."""
+        if cfg_strength < 1e-5:
+            raise NotImplementedError("cfg_strength < 1e-5 (single-branch sampling, cfm.py:170-171) is not on the served path")
+        layout = build_layout([u.n for u in utts])
+        ws = self.upload(utts, layout, steps, sway_sampling_coef)
+        self.hoist(ws, steps)
+        self.run_steps(ws, steps, cfg_strength)
+        ops.where_rows(ws.x, ws.cond, ws.cond_flag, self.cfg.mel_dim)        # cfm.py:204
+        return ws, layout
+
+    def forward_flow(self, utts: list[UtteranceInput], t: float) -> list[torch.Tensor]:
+        """One CFG velocity evaluation pair at time t (test hook): returns per utterance [2, n, mel] (cond, null)."""
+        layout = build_layout([u.n for u in utts])
+        ws = self.upload(utts, layout, 1, None)
+        ws.tgrid[0] = t
+        self.hoist(ws, 1)
+        graphs, self.use_graphs = self.use_graphs, False
+        ws.dts.zero_()
+        self.step(ws, 0, 2.0)
+        self.use_graphs = graphs
+        torch.cuda.synchronize()
+        R, mel = ws.R, self.cfg.mel_dim
+        return [torch.stack((ws.pred[s:s + n, :mel], ws.pred[R + s:R + s + n, :mel])).clone()
+                for s, n in zip(layout.starts, layout.lengths)]

@@ -69,16 +69,18 @@ def gemm(A: torch.Tensor, B: torch.Tensor, *, M: int | None = None, N: int | Non
 
 
 def attention(qkv: torch.Tensor, tiles: torch.Tensor, out: torch.Tensor, heads: int, q_col: int, k_col: int, v_col: int,
-              softmax_scale: float = 0.125, variant: int = 0, vt: torch.Tensor | None = None) -> None:
+              softmax_scale: float = 0.125) -> None:
     assert qkv.dtype == BF16 and out.dtype == BF16 and tiles.dtype == I32 and tiles.is_contiguous() and tiles.shape[1] == 4
     call("f5_attention_d64", ptr(qkv), _ld(qkv), qkv.shape[0], q_col, k_col, v_col, heads, ptr(tiles), tiles.shape[0],
-         ptr(out), _ld(out), float(softmax_scale), variant, ptr(vt), _ld(vt) if vt is not None else 0, stream_ptr())
+         ptr(out), _ld(out), float(softmax_scale), stream_ptr())
 
 
-def layernorm_mod(x: torch.Tensor, y: torch.Tensor, a: torch.Tensor, b: torch.Tensor, a_off: float, eps: float = 1e-6,
-                  M: int | None = None) -> None:
-    assert x.dtype == F32 and y.dtype == BF16 and a.dtype == F32 and b.dtype == F32
-    call("f5_layernorm_mod", ptr(x), _ld(x), ptr(y), _ld(y), x.shape[0] if M is None else M, x.shape[1], ptr(a), ptr(b),
+def layernorm_mod(x: torch.Tensor, y: torch.Tensor | None, a: torch.Tensor, b: torch.Tensor, a_off: float, eps: float = 1e-6,
+                  M: int | None = None, y32: torch.Tensor | None = None) -> None:
+    assert x.dtype == F32 and a.dtype == F32 and b.dtype == F32
+    assert (y is None or y.dtype == BF16) and (y32 is None or y32.dtype == F32)
+    call("f5_layernorm_mod", ptr(x), _ld(x), ptr(y), _ld(y) if y is not None else 0, ptr(y32),
+         _ld(y32) if y32 is not None else 0, x.shape[0] if M is None else M, x.shape[1], ptr(a), ptr(b),
          float(a_off), float(eps), stream_ptr())
 
 
