@@ -60,7 +60,7 @@ class CFM:
         self.vocab_char_map = vocab_char_map
         self.num_channels = cfg.mel_dim
         self.engine = F5Engine(state_dict, cfg, device)
-        self._device = torch.device(device)
+        self._device = self.engine.device
 
     @property
     def device(self):
@@ -275,10 +275,10 @@ class Synthesizer:
         return _Prepared(audio, rms, ref_len, tokens, duration, spec.noise_index)
 
     @torch.inference_mode()
-    def generate(self, specs: list[UtteranceSpec], nfe_step=nfe_step, cfg_strength=cfg_strength,
-                 sway_sampling_coef=sway_sampling_coef, speed=speed, fix_duration=fix_duration, y0: list | None = None,
-                 return_mel: bool = False):
-        """-> list of np.float32 waves (and optionally list of np mel [100, F_gen])."""
+    def generate_device(self, specs: list[UtteranceSpec], nfe_step=nfe_step, cfg_strength=cfg_strength,
+                        sway_sampling_coef=sway_sampling_coef, speed=speed, fix_duration=fix_duration,
+                        y0: list | None = None):
+        """Host inputs -> device waveforms.  Returns (wav_flat fp32 on device, offsets, frames, ws, layout, preps)."""
         from .synthetic import initial_noise
         model, dev = self.model, self.device
         preps = [self._prep(s, speed, fix_duration) for s in specs]
@@ -296,11 +296,12 @@ class Synthesizer:
                 mels[i] = m[j]
         ids = T.list_str_to_idx([p.tokens for p in preps], model.vocab_char_map)
         noise = y0 if y0 is not None else [initial_noise(4096, p.noise_index) for p in preps]
-        utts = model._prepare(torch.nn.utils.rnn.pad_sequence(mels, batch_first=True) if len({m.shape[0] for m in mels}) > 1
-                              else torch.stack(mels), ids, torch.tensor([p.duration for p in preps]),
-                              torch.tensor([m.shape[0] for m in mels]), None, 4096, None, noise)
-        for u, m in zip(utts, mels):
-            u.cond = m                                                            # un-padded device mel
+        utts = []
+        for p, m, row, nz in zip(preps, mels, ids, noise):                        # CFM.sample prologue, cfm.py:110-138
+            tid = row[row != -1]
+            lens_i = max(int(tid.numel()), m.shape[0])
+            n = min(max(lens_i + 1, p.duration), 4096)
+            utts.append(UtteranceInput(cond=m, text_ids=tid, n=n, cond_len=lens_i, y0=nz))
         ws, layout = model.engine.sample_packed(utts, steps=nfe_step, cfg_strength=cfg_strength,
                                                 sway_sampling_coef=sway_sampling_coef)
         h2d += ws.h2d_bytes
@@ -314,6 +315,16 @@ class Synthesizer:
         gains = torch.tensor([p.rms / target_rms if p.rms < target_rms else 1.0 for p in preps], dtype=torch.float32)
         h2d += src_rows.numel() * 4 + pos.numel() * 4 + gains.numel() * 4
         wav = veng.decode_rows(ws.x, src_rows.to(dev), pos.to(dev), starts, frames, offs, tot, gains.to(dev))  # :475-476 fused
+        self.last_h2d_bytes = h2d
+        return wav, offs, frames, tot, ws, layout, preps
+
+    @torch.inference_mode()
+    def generate(self, specs: list[UtteranceSpec], nfe_step=nfe_step, cfg_strength=cfg_strength,
+                 sway_sampling_coef=sway_sampling_coef, speed=speed, fix_duration=fix_duration, y0: list | None = None,
+                 return_mel: bool = False):
+        """-> list of np.float32 waves (and optionally list of np mel [100, F_gen]); host in, host out."""
+        wav, offs, frames, tot, ws, layout, preps = self.generate_device(specs, nfe_step, cfg_strength, sway_sampling_coef,
+                                                                         speed, fix_duration, y0)
         host = torch.empty(tot, dtype=torch.float32).pin_memory()
         host.copy_(wav[:tot], non_blocking=True)                                  # D2H (:479)
         mel_out = None
@@ -321,7 +332,7 @@ class Synthesizer:
             mel_out = [ws.x[ls + p.ref_len: ls + n, :n_mel_channels].t().cpu().numpy()
                        for ls, n, p in zip(layout.starts, layout.lengths, preps)]
         torch.cuda.current_stream().synchronize()
-        self.last_h2d_bytes, self.last_d2h_bytes = h2d, tot * 4
+        self.last_d2h_bytes = tot * 4
         waves = [host[o:o + 256 * (T_ - 1)].numpy() for o, T_ in zip(offs, frames)]
         return (waves, mel_out) if return_mel else waves
 

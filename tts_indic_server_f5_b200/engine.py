@@ -171,11 +171,14 @@ class F5Engine:
         from ._lib import lib
         if not torch.cuda.is_available():
             raise RuntimeError("F5Engine needs a CUDA device (sm_100a); there is no CPU fallback")
-        torch.cuda.set_device(torch.device(device))
+        dev = torch.device(device)
+        if dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+        torch.cuda.set_device(dev)
         rc = lib.f5_device_check()
         if rc != 0:
             raise RuntimeError("libf5b200.so targets sm_100a (B200) only")
-        self.cfg, self.device = cfg, torch.device(device)
+        self.cfg, self.device = cfg, dev
         self.w = DiTWeights(sd, cfg, self.device)
         self.use_graphs = use_graphs
         self._ws: dict[int, Workspace] = {}

@@ -23,7 +23,10 @@ class VocosEngine:
         from ._lib import lib
         if not torch.cuda.is_available() or lib.f5_device_check() != 0:
             raise RuntimeError("VocosEngine needs a B200 (sm_100a); there is no CPU fallback")
-        self.cfg, self.device = vcfg, torch.device(device)
+        device = torch.device(device)
+        if device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        self.cfg, self.device = vcfg, device
         C, I = vcfg.dim, vcfg.intermediate_dim
         assert vcfg.n_fft == 1024 and vcfg.hop == 256 and C % 128 == 0 and C <= 512 and vcfg.n_mels <= MELP
         bf = lambda t: t.to(device=device, dtype=BF16).contiguous()      # noqa: E731
