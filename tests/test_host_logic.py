@@ -1,0 +1,167 @@
+"""CPU: host-side logic of the product (text front-end, packed layout, sharding, weight layouts, C ABI surface)."""
+import ctypes
+import os
+import re
+import subprocess
+import tempfile
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from tts_indic_server_f5_b200 import text as T
+from tts_indic_server_f5_b200 import weights as W
+from tts_indic_server_f5_b200.dist import lpt_partition, utterance_cost
+from tts_indic_server_f5_b200.layout import GAP, build_layout
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_tokenizer_one_token_per_codepoint_and_vocab_roundtrip(tmp_path):
+    toks = T.synthetic_indic_vocab()
+    assert toks[0] == " " and len(toks) == len(set(toks)) == W.INDICF5.vocab_size
+    p = tmp_path / "vocab.txt"
+    T.write_vocab(str(p), toks)
+    vmap, size = T.get_tokenizer(str(p), "custom")
+    assert size == len(toks) and vmap[" "] == 0 and vmap["ಕ"] == toks.index("ಕ")
+    s = "ಕನ್ನಡ ಪದ, हिन्दी."
+    out = T.convert_char_to_pinyin([s])[0]
+    assert out == list(s)                                   # virama / matras are separate tokens, spaces preserved
+    ids = T.list_str_to_idx([out, out[:3]], vmap)
+    assert ids.shape == (2, len(s)) and (ids[1, 3:] == -1).all() and (ids[0] >= 0).all()
+    assert T.list_str_to_idx([["一x"]], vmap)[0, 0] == 0   # unknown -> 0
+    with pytest.raises(ValueError):
+        T.convert_char_to_pinyin(["中文"])
+    assert T.convert_char_to_pinyin(["ಕ;ab"])[0] == ["ಕ", ",", " ", "a", "b"]   # ';'->',' and ASCII-run leading space
+
+
+def test_duration_and_ref_text_rules():
+    assert T.finish_ref_text("abc") == "abc. " and T.finish_ref_text("abc.") == "abc. " and T.finish_ref_text("abc. ") == "abc. "
+    assert T.estimate_duration(468, "x" * 100, "y" * 50) == 468 + 234
+    assert T.estimate_duration(468, "x" * 100, "y" * 50, speed=2.0) == 468 + 117
+    assert T.estimate_duration(468, "r", "g", fix_duration=10.0) == int(10.0 * 24000 / 256)
+    assert T.chunk_text("a. b. c.", 3) == ["a.", "b.", "c."]
+    assert T.chunk_text("", 10) == []
+
+
+def test_layout_invariants():
+    lens = [120, 1, 300, 129]
+    L = build_layout(lens)
+    R = L.half_rows
+    assert R % 128 == 0 and L.row_pos.numel() == 2 * R
+    pos = L.row_pos[:R]
+    assert torch.equal(L.row_pos[R:], pos)
+    for s, n in zip(L.starts, lens):
+        assert torch.equal(pos[s:s + n], torch.arange(n, dtype=torch.int32))
+        assert (pos[s - GAP:s] == -1).all() and (pos[s + n:s + n + GAP] == -1).all()
+    assert int((pos >= 0).sum()) == sum(lens)
+    # every real row is covered by exactly one query tile per half; kv ranges are the utterance's own rows
+    cover = torch.zeros(2 * R, dtype=torch.int32)
+    for q0, kv0, kvl, qv in L.attn_tiles.tolist():
+        cover[q0:q0 + qv] += 1
+        assert (L.row_pos[kv0:kv0 + kvl] == torch.arange(kvl, dtype=torch.int32)).all()
+        assert kv0 <= q0 < kv0 + kvl
+    assert torch.equal(cover, (L.row_pos >= 0).to(torch.int32))
+    assert L.seg_rows.tolist() == [[h + s, n] for h in (0, R) for s, n in zip(L.starts, lens)]
+
+
+def test_lpt_partition_balances_and_covers():
+    g = torch.Generator().manual_seed(0)
+    lens = torch.randint(1029, 1410, (512,), generator=g).tolist()
+    for w in (1, 2, 4, 8):
+        parts = lpt_partition(lens, w)
+        assert sorted(i for p in parts for i in p) == list(range(512))
+        loads = [sum(utterance_cost(lens[i]) for i in p) for p in parts]
+        assert max(loads) / (sum(loads) / w) < 1.02          # <2 % imbalance at 64 utterances / GPU
+
+
+def test_conv_pos_weight_block_diagonal_is_exact():
+    from tts_indic_server_f5_b200.engine import _conv_pos_weight
+    D, G, K, n = 256, 16, 31, 50
+    g = torch.Generator().manual_seed(1)
+    w = torch.randn(D, D // G, K, generator=g)
+    x = torch.randn(n, D, generator=g)
+    ref = F.conv1d(x.t()[None], w, None, padding=K // 2, groups=G)[0].t()
+    wt = _conv_pos_weight(w).reshape(K, D, 64)
+    xp = F.pad(x, (0, 0, K // 2, K // 2))
+    out = torch.zeros(n, D)
+    for t in range(K):
+        for sg in range(D // 64):
+            out[:, sg * 64:(sg + 1) * 64] += xp[t:t + n, sg * 64:(sg + 1) * 64] @ wt[t, sg * 64:(sg + 1) * 64].t()
+    torch.testing.assert_close(out, ref, rtol=1e-4, atol=1e-4)
+
+
+def test_checkpoint_key_rules_and_config_inference():
+    cfg = W.tiny_dit_config()
+    sd = W.make_dit_state_dict(cfg, seed=2)
+    ckpt = {"ema_model_state_dict": {**{"ema_model." + k: v for k, v in sd.items()}, "initted": torch.tensor(1), "step": torch.tensor(5),
+                                     "ema_model.mel_spec.mel_stft.mel_scale.fb": torch.zeros(1)}}
+    out = W.strip_checkpoint(ckpt)
+    assert set(out) == set(sd)
+    assert W.infer_dit_config(out) == cfg
+    assert W.make_dit_state_dict(cfg, seed=2)["transformer.proj_out.weight"].equal(sd["transformer.proj_out.weight"])
+    full = W.make_dit_state_dict(W.INDICF5, seed=0)
+    assert full["transformer.transformer_blocks.21.attn_norm.linear.weight"].shape == (6144, 1024)
+    assert full["transformer.input_embed.proj.weight"].shape == (1024, 712)
+    assert full["transformer.input_embed.conv_pos_embed.conv1d.2.weight"].shape == (1024, 64, 31)
+
+
+def test_sway_grid_matches_oracle_and_closed_form():
+    from oracle import f5_oracle as O
+    from tts_indic_server_f5_b200.engine import sway_time_grid
+    t = sway_time_grid(32, -1.0)
+    assert torch.equal(t, O.sway_time_grid(32, -1.0))
+    i = torch.arange(33, dtype=torch.float64)
+    torch.testing.assert_close(t.double(), 1 - torch.cos(torch.pi * i / 64), rtol=0, atol=2e-7)
+    assert torch.equal(sway_time_grid(8, None), torch.linspace(0, 1, 9))
+
+
+# ------------------------------------------------------------------------------------------------ C ABI surface
+def _declared_symbols():
+    h = open(os.path.join(ROOT, "include", "f5_b200.h")).read()
+    return sorted(set(re.findall(r"^(?:int|const char\*)\s+(f5_\w+)\s*\(", h, flags=re.M)))
+
+
+def test_library_exports_every_declared_symbol():
+    from tts_indic_server_f5_b200 import _lib
+    syms = _declared_symbols()
+    assert len(syms) >= 16 and sorted(_lib.EXPORTS) == syms
+    for s in syms:
+        assert hasattr(_lib.lib, s)
+    assert b"sm_100a" in _lib.lib.f5_version()
+
+
+def test_gemm_args_struct_layout_matches_header():
+    from tts_indic_server_f5_b200 import _lib
+    src = '#include <stdio.h>\n#include <stddef.h>\n#include "f5_b200.h"\nint main(){printf("%zu %zu %zu %zu", sizeof(f5_gemm_args),' \
+          ' offsetof(f5_gemm_args, mode), offsetof(f5_gemm_args, resid), offsetof(f5_gemm_args, num_sms));return 0;}'
+    with tempfile.TemporaryDirectory() as d:
+        c = os.path.join(d, "s.c")
+        open(c, "w").write(src)
+        exe = os.path.join(d, "s")
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe])
+        size, o_mode, o_resid, o_sms = map(int, subprocess.check_output([exe]).split())
+    G = _lib.GemmArgs
+    assert (ctypes.sizeof(G), G.mode.offset, G.resid.offset, G.num_sms.offset) == (size, o_mode, o_resid, o_sms)
+
+
+def test_launchers_reject_bad_arguments_without_touching_the_gpu():
+    from tts_indic_server_f5_b200 import _lib
+    a = _lib.GemmArgs()
+    assert _lib.lib.f5_gemm_bf16(ctypes.byref(a), None) == -1            # F5_ERR_ARG: null operands
+    a.A, a.B, a.M, a.N, a.num_taps, a.kc_per_tap, a.block_n = 1 << 20, 1 << 21, 128, 100, 1, 1, 256
+    assert _lib.lib.f5_gemm_bf16(ctypes.byref(a), None) == -1            # N % 8 != 0
+    assert _lib.lib.f5_layernorm_mod(None, 0, None, 0, None, 0, 1, 128, None, None, 1.0, 1e-6, None) == -1
+    assert _lib.lib.f5_attention_d64(None, 0, 0, 0, 0, 0, 16, None, 0, None, 0, 0.125, None) == -1
+    with pytest.raises(_lib.F5Error):
+        _lib.check(-2, "x")
+
+
+def test_engine_refuses_to_run_without_cuda():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from tts_indic_server_f5_b200 import api
+    with pytest.raises(RuntimeError):
+        api.load_model(device="cpu")
+    with pytest.raises(RuntimeError):
+        api.load_model(device="cuda")

@@ -1,0 +1,104 @@
+"""CPU: the oracle (oracle/f5_oracle.py) against the golden vectors minted from the REAL reference (oracle/make_golden.py),
+and, where /root/reference exists, against the reference's own modules executed in place."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import f5_oracle as O
+from oracle import ref_shims as R
+from tts_indic_server_f5_b200 import synthetic as S
+from tts_indic_server_f5_b200 import text as T
+from tts_indic_server_f5_b200 import weights as W
+
+
+@pytest.fixture(scope="module")
+def tiny():
+    cfg, vcfg = W.tiny_dit_config(), W.tiny_vocos_config()
+    return cfg, vcfg, W.make_dit_state_dict(cfg, seed=1), W.make_vocos_state_dict(vcfg, seed=1)
+
+
+def _ids(spec):
+    vocab = {t: i for i, t in enumerate(T.synthetic_indic_vocab())}
+    ref_text = spec.ref_text + (" " if len(spec.ref_text[-1].encode()) == 1 else "")
+    return O.list_str_to_idx(T.convert_char_to_pinyin([ref_text + spec.gen_text]), vocab)
+
+
+def test_oracle_forward_matches_golden(tiny, golden_dir):
+    cfg, _, sd, _ = tiny
+    g = np.load(os.path.join(golden_dir, "tiny.npz"))
+    x, cond, text = (torch.from_numpy(g[k])[None] for k in ("fwd_x", "fwd_condin", "fwd_text"))
+    with torch.inference_mode():
+        a = O.dit_forward(sd, cfg, x, cond, text, torch.tensor(0.37), False, False)[0].numpy()
+        b = O.dit_forward(sd, cfg, x, cond, text, torch.tensor(0.37), True, True)[0].numpy()
+    np.testing.assert_allclose(a, g["fwd_cond"], rtol=0, atol=2e-5)   # fp32 CPU, same op order: round-off only
+    np.testing.assert_allclose(b, g["fwd_null"], rtol=0, atol=2e-5)
+
+
+@pytest.mark.parametrize("wl,i", [("tiny", 0), ("tiny3", 1), ("tiny3", 2)])
+def test_oracle_end_to_end_matches_golden(tiny, golden_dir, wl, i):
+    cfg, vcfg, sd, vsd = tiny
+    g = np.load(os.path.join(golden_dir, "tiny.npz"))
+    spec = S.workload(wl)[i]
+    with torch.inference_mode():
+        wave, mel = O.infer_one(sd, cfg, vsd, vcfg, spec.audio, _ids(spec), spec.duration,
+                                y0=S.initial_noise(4096, spec.noise_index))
+    ref_len = spec.meta["ref_len"]
+    np.testing.assert_allclose(mel.numpy().T, g[f"{wl}_{i}_mel"][ref_len:], rtol=0, atol=1e-4)
+    np.testing.assert_allclose(wave.numpy(), g[f"{wl}_{i}_wave"], rtol=0, atol=1e-5)
+
+
+def test_oracle_prompt_mel_matches_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "tiny.npz"))
+    m = O.mel_spectrogram(S.prompt_audio(0.6, 0))[0].numpy()
+    np.testing.assert_allclose(m, g["prompt_mel"], rtol=0, atol=1e-5)
+
+
+def test_product_mel_frontend_matches_oracle():
+    from tts_indic_server_f5_b200.melspec import mel_spectrogram
+    w = S.prompt_audio(1.0, 3)
+    np.testing.assert_allclose(mel_spectrogram(w).numpy(), O.mel_spectrogram(w).numpy(), rtol=0, atol=1e-5)
+
+
+@pytest.mark.skipif(not R.reference_available(), reason="reference tree only exists in the build container")
+def test_oracle_vs_real_reference_modules(tiny):
+    """Same weights, same inputs, reference's own DiT / CFM.sample vs the restatement."""
+    cfg, _, sd, _ = tiny
+    cfm = R.build_reference_cfm(sd, cfg)
+    g = torch.Generator().manual_seed(3)
+    n, F_ = 70, 30
+    cond = torch.randn(1, F_, 100, generator=g)
+    text = torch.randint(0, cfg.vocab_size, (1, 41), generator=g)
+    with torch.inference_mode():
+        ref, _ = cfm.sample(cond=cond, text=text, duration=n, steps=6, cfg_strength=2.0, sway_sampling_coef=-1.0, seed=11)
+        ours = O.cfm_sample(sd, cfg, cond, text, n, steps=6, seed=11)
+    assert torch.equal(ref, ours)
+    # text longer than the prompt: lens = max(text_lens, lens) (cfm.py:123-125), duration = lens + 1 floor (:136)
+    text2 = torch.randint(0, cfg.vocab_size, (1, 50), generator=g)
+    with torch.inference_mode():
+        ref, _ = cfm.sample(cond=cond[:, :20], text=text2, duration=10, steps=3, cfg_strength=2.0, sway_sampling_coef=-1.0, seed=5)
+        ours = O.cfm_sample(sd, cfg, cond[:, :20], text2, 10, steps=3, seed=5)
+    assert ref.shape[1] == 51 and torch.equal(ref, ours)
+
+
+@pytest.mark.skipif(not R.reference_available(), reason="reference tree only exists in the build container")
+def test_text_frontend_vs_reference():
+    ref = R.load_reference()
+    texts = [S.workload("tiny3")[1].ref_text + "ನಮಸ್ಕಾರ, हिन्दी! ", "ಕನ್ನಡ; “quote” ‘x’ ಪದ?", "अ आ इ. ई"]
+    assert T.convert_char_to_pinyin(texts) == ref.model_utils.convert_char_to_pinyin(texts)
+    long = " ".join(T.synthetic_indic_text(40, i) + "." for i in range(12))
+    for mc in (60, 135, 400):
+        assert T.chunk_text(long, mc) == ref.utils_infer.chunk_text(long, mc)
+    vocab = {t: i for i, t in enumerate(T.synthetic_indic_vocab())}
+    toks = T.convert_char_to_pinyin(texts)
+    assert torch.equal(T.list_str_to_idx(toks, vocab), ref.model_utils.list_str_to_idx(toks, vocab))
+
+
+@pytest.mark.skipif(os.environ.get("F5_SKIP_SLOW") == "1", reason="~1 min of CPU")
+def test_oracle_full_size_forward_is_finite_and_param_count():
+    """Architecture pin: 337.10 M parameters with the vendored 2545-entry vocab."""
+    cfg = W.DiTConfig(vocab_size=2545)
+    sd = W.make_dit_state_dict(cfg, seed=0)
+    n_params = sum(v.numel() for v in sd.values())
+    assert abs(n_params - 337.10e6) < 0.02e6, n_params

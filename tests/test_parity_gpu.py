@@ -1,0 +1,198 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI (ops -> libf5b200.so), against
+  * the golden vectors minted from the REAL reference (tests/golden/*.npz, oracle/make_golden.py),
+  * the oracle (CPU fp32 restatement) on seeded inputs at sizes it finishes in seconds,
+  * size-independent properties at the full IndicF5 size (packing invariance, graph == eager, ISTFT perfect reconstruction).
+
+Tolerances (bf16 tensor-core operands; fp32 accumulation, residual stream, LayerNorm, softmax, ODE state, ISTFT):
+  mel   rel-L2 <= 1.0e-2, L-inf <= 6e-2 on a +-5 range    (measured 3.1e-3..3.9e-3 / 0.013..0.019)
+  wave  SNR    >= 40 dB                                    (measured 44.7..50.1 dB)
+For scale: the reference's OWN bf16 mode (whole-module .to(bfloat16)) sits at rel-L2 1.33e-2, L-inf 0.156 from its fp32
+result on the tiny case (tests/golden/ref_bf16_error.json) — the CUDA path must be at least that close, and is ~4x closer.
+There is no separate fp32-operand mode in this round (TF32/3xTF32 GEMM variants are future work)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+MEL_REL, MEL_LINF, WAVE_SNR = 1.0e-2, 6e-2, 40.0
+
+if torch.cuda.is_available():
+    from oracle import f5_oracle as O
+    from tts_indic_server_f5_b200 import api, ops, synthetic as S, text as T, weights as W
+    from tts_indic_server_f5_b200.engine import UtteranceInput
+
+
+def rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.linalg.norm(a - b) / np.linalg.norm(b))
+
+
+def snr(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(10 * np.log10((b ** 2).sum() / max(((a - b) ** 2).sum(), 1e-30)))
+
+
+@pytest.fixture(scope="module")
+def tiny_models():
+    cfg, vcfg = W.tiny_dit_config(), W.tiny_vocos_config()
+    sd, vsd = W.make_dit_state_dict(cfg, seed=1), W.make_vocos_state_dict(vcfg, seed=1)
+    return cfg, vcfg, sd, vsd, api.load_model(state_dict=sd), api.load_vocoder(state_dict=vsd)
+
+
+@pytest.fixture(scope="module")
+def full_models():
+    model = api.load_model(state_dict=W.make_dit_state_dict(W.INDICF5, seed=0))
+    voc = api.load_vocoder(state_dict=W.make_vocos_state_dict(W.VOCOS_24K, seed=0))
+    return model, voc
+
+
+def test_native_library_is_the_path():
+    from tts_indic_server_f5_b200 import _lib
+    assert _lib.lib.f5_device_check() == 0 and os.path.basename(_lib.LIB) == "libf5b200.so"
+
+
+def test_tiny_forward_pair_vs_reference_golden(tiny_models, golden_dir):
+    *_, model, _ = tiny_models
+    g = np.load(os.path.join(golden_dir, "tiny.npz"))
+    u = UtteranceInput(cond=torch.from_numpy(g["fwd_condin"]), text_ids=torch.from_numpy(g["fwd_text"]), n=96, cond_len=96,
+                       y0=torch.from_numpy(g["fwd_x"]))
+    pc = model.engine.forward_flow([u], 0.37)[0].cpu().numpy()
+    assert rel(pc[0], g["fwd_cond"]) < MEL_REL and rel(pc[1], g["fwd_null"]) < MEL_REL
+    assert np.abs(pc[0] - g["fwd_cond"]).max() < MEL_LINF
+
+
+@pytest.mark.parametrize("wl", ["tiny", "tiny3"])
+def test_tiny_end_to_end_vs_reference_golden(tiny_models, golden_dir, wl):
+    *_, model, voc = tiny_models
+    g = np.load(os.path.join(golden_dir, "tiny.npz"))
+    bf16_ref = json.load(open(os.path.join(golden_dir, "ref_bf16_error.json")))["tiny"]
+    specs = S.workload(wl)
+    waves, mels = api.Synthesizer(model, voc).generate(specs, return_mel=True)
+    for i, (spec, wv, ml) in enumerate(zip(specs, waves, mels)):
+        gm = g[f"{wl}_{i}_mel"][spec.meta["ref_len"]:]
+        assert ml.shape == gm.T.shape and wv.shape == g[f"{wl}_{i}_wave"].shape
+        r, li, s = rel(ml.T, gm), float(np.abs(ml.T - gm).max()), snr(wv, g[f"{wl}_{i}_wave"])
+        print(f"{wl}[{i}] mel rel-L2 {r:.2e} L-inf {li:.3f} wave SNR {s:.1f} dB")
+        assert r < MEL_REL and li < MEL_LINF and s > WAVE_SNR
+        assert r < bf16_ref["mel_rel_l2"] and li < bf16_ref["mel_linf"]      # no worse than the reference's own bf16 mode
+
+
+def test_full_size_c1_vs_reference_golden(full_models, golden_dir):
+    model, voc = full_models
+    g = np.load(os.path.join(golden_dir, "full_c1.npz"))
+    spec = S.workload("c1")
+    waves, mels = api.Synthesizer(model, voc).generate(spec, return_mel=True)
+    gm = g["mel"][spec[0].meta["ref_len"]:]
+    r, li, s = rel(mels[0].T, gm), float(np.abs(mels[0].T - gm).max()), snr(waves[0], g["wave"])
+    print(f"full C1: mel rel-L2 {r:.2e} L-inf {li:.3f} wave SNR {s:.1f} dB")
+    assert r < MEL_REL and li < MEL_LINF and s > WAVE_SNR
+    wv = voc.decode(torch.from_numpy(gm.T[None].copy()))[0].cpu().numpy()      # vocoder alone on the reference's mel
+    assert snr(wv, g["wave"]) > 43.0
+
+
+def test_cfm_sample_api_vs_oracle(tiny_models):
+    """`CFM.sample` surface (cfm.py:82-99): raw-wave cond, list-of-str text, seed, lens/duration rules, edit_mask."""
+    cfg, _, sd, _, model, _ = tiny_models
+    vocab = {t: i for i, t in enumerate(T.synthetic_indic_vocab())}
+    audio = S.prompt_audio(0.5, 1)
+    texts = [T.convert_char_to_pinyin([T.synthetic_indic_text(30, 4)])[0]]
+    out, traj = model.sample(cond=audio, text=texts, duration=90, steps=8, cfg_strength=2.0, sway_sampling_coef=-1.0, seed=3)
+    ids = O.list_str_to_idx(texts, vocab)
+    with torch.inference_mode():
+        ref = O.cfm_sample(sd, cfg, O.mel_spectrogram(audio).permute(0, 2, 1), ids, 90, steps=8, seed=3)
+    assert out.shape == ref.shape == (1, 90, 100) and traj.shape == (1, 1, 90, 100)
+    assert rel(out.cpu().numpy(), ref.numpy()) < MEL_REL
+    # text longer than the mel: cond_mask extends, duration floor lens + 1 (cfm.py:123-137)
+    long_text = [T.convert_char_to_pinyin([T.synthetic_indic_text(70, 5)])[0]]
+    out2, _ = model.sample(cond=audio, text=long_text, duration=10, steps=4, cfg_strength=2.0, seed=1)
+    with torch.inference_mode():
+        ref2 = O.cfm_sample(sd, cfg, O.mel_spectrogram(audio).permute(0, 2, 1), O.list_str_to_idx(long_text, vocab), 10, steps=4,
+                            seed=1, sway_sampling_coef=None)
+    assert out2.shape == ref2.shape == (1, 71, 100) and rel(out2.cpu().numpy(), ref2.numpy()) < MEL_REL
+    # batch of two ragged items == each item alone (batch-1 semantics), zero rows past an item's duration
+    mel = O.mel_spectrogram(audio).permute(0, 2, 1)
+    y0 = [S.initial_noise(120, 0), S.initial_noise(120, 1)]
+    outb, _ = model.sample(cond=torch.cat([mel, mel]), text=[texts[0], long_text[0]], duration=torch.tensor([80, 110]), steps=4,
+                           cfg_strength=2.0, sway_sampling_coef=-1.0, y0=y0)
+    o0, _ = model.sample(cond=mel, text=[texts[0]], duration=80, steps=4, cfg_strength=2.0, sway_sampling_coef=-1.0, y0=y0[:1])
+    assert outb.shape == (2, 110, 100) and float(outb[0, 80:].abs().max()) == 0.0
+    assert rel(outb[0, :80].cpu().numpy(), o0[0].cpu().numpy()) < 1e-4      # GRN's atomic sums are the only order-dependent op
+    for bad in (dict(duplicate_test=True), dict(cfg_strength=0.0)):
+        with pytest.raises(NotImplementedError):
+            model.sample(cond=mel, text=[texts[0]], duration=80, **bad)
+
+
+def test_vocos_decode_vs_oracle(tiny_models):
+    _, vcfg, _, vsd, _, voc = tiny_models
+    g = torch.Generator().manual_seed(9)
+    for B, T_ in ((1, 2), (3, 257), (2, 64)):
+        mel = torch.randn(B, 100, T_, generator=g) * 2 - 4
+        got = voc.decode(mel).cpu().numpy()
+        with torch.inference_mode():
+            ref = O.vocos_decode(vsd, vcfg, mel).numpy()
+        assert got.shape == ref.shape == (B, 256 * (T_ - 1))
+        assert snr(got, ref) > WAVE_SNR, (B, T_, snr(got, ref))
+
+
+def test_istft_perfect_reconstruction_property():
+    """Size-independent property of the ISTFT kernels: analysing a signal with the matching STFT and feeding
+    (log|X|, angle X) back reconstructs the signal (hann, hop = n_fft/4 satisfies COLA)."""
+    g = torch.Generator().manual_seed(2)
+    x = (torch.randn(1, 256 * 300, generator=g) * 0.1).cuda()
+    win = torch.hann_window(1024, device="cuda")
+    X = torch.stft(x, 1024, 256, 1024, win, center=True, return_complex=True)[0].t()       # [T, 513]
+    T_ = X.shape[0]
+    spec = torch.zeros(T_, 1152, device="cuda")
+    spec[:, :513] = X.abs().clamp_min(1e-30).log()
+    spec[:, 513:1026] = X.angle()
+    frames = torch.zeros(T_, 1024, device="cuda")
+    wav = torch.zeros(256 * (T_ - 1), device="cuda")
+    seg = torch.tensor([[0, T_, 0, 0]], dtype=torch.int32, device="cuda")
+    ops.istft(spec, win, frames, seg, wav.numel(), wav)
+    torch.cuda.synchronize()
+    assert snr(wav.cpu().numpy(), x[0, : wav.numel()].cpu().numpy()) > 90.0
+
+
+def test_packing_invariance_and_graph_equals_eager_full_size(full_models):
+    """At the full IndicF5 size: an utterance sampled inside a ragged packed batch equals the same utterance sampled
+    alone (per-utterance semantics: attention / conv halo / GRN never cross utterances), and CUDA-graph replay equals
+    eager launches bit for bit."""
+    model, voc = full_models
+    syn = api.Synthesizer(model, voc)
+    specs = S.workload("small8")
+    waves = syn.generate(specs, nfe_step=4)
+    alone = syn.generate([specs[3]], nfe_step=4)[0]
+    assert alone.shape == waves[3].shape and snr(waves[3], alone) > 70.0
+    assert all(np.isfinite(w).all() and np.abs(w).max() > 0 for w in waves)
+    model.engine.use_graphs = False
+    try:
+        eager = syn.generate(specs, nfe_step=4)
+    finally:
+        model.engine.use_graphs = True
+    again = syn.generate(specs, nfe_step=4)
+    assert all(np.array_equal(a, b) for a, b in zip(eager, again))
+
+
+def test_infer_process_and_manager_surface(tiny_models, tmp_path):
+    """Boundary #2 / #1 surface: infer_process (chunking + cross-fade) and the TTSManager contract."""
+    import wave as wavmod
+    *_, model, voc = tiny_models
+    audio = S.prompt_audio(1.0, 2)
+    p = str(tmp_path / "ref.wav")
+    with wavmod.open(p, "wb") as w:
+        w.setnchannels(1); w.setsampwidth(2); w.setframerate(24000)
+        w.writeframes((audio[0].numpy() * 32767).astype("<i2").tobytes())
+    ref_text = T.finish_ref_text(T.synthetic_indic_text(20, 1))
+    gen = ". ".join(T.synthetic_indic_text(60, 10 + i) for i in range(4)) + "."
+    wave, sr, mel = api.infer_process(p, ref_text, gen, model, voc, nfe_step=4)
+    assert sr == 24000 and wave.ndim == 1 and mel.shape[0] == 100 and np.isfinite(wave).all()
+    nchunks = len(T.chunk_text(gen, int(len(ref_text.encode()) / 1.0 * 24)))
+    assert nchunks >= 2 and len(wave) == 256 * (mel.shape[1] - nchunks) - (nchunks - 1) * 3600
+    mgr = api.TTSManager()
+    assert not mgr.model
+    with pytest.raises(ValueError, match="TTS model not loaded"):
+        mgr.synthesize("x", p, ref_text)

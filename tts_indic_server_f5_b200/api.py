@@ -242,6 +242,23 @@ class _Prepared:
     noise_index: int
 
 
+@dataclass
+class Staged:
+    """One request batch resident on the device (output of `Synthesizer.stage`)."""
+    ws: object
+    layout: object
+    preps: list
+    frames: list
+    offs: list
+    total: int
+    src_rows: torch.Tensor
+    vpos: torch.Tensor
+    gains: torch.Tensor
+    seg: torch.Tensor
+    nfe_step: int
+    h2d_bytes: int
+
+
 class Synthesizer:
     """Batched synthesis over (model, vocoder): the tensor part of `infer_batch_process` (utils_infer.py:423-482) for
     many independent utterances at once.  Inputs are host objects, outputs are host numpy arrays."""
@@ -275,20 +292,19 @@ class Synthesizer:
         return _Prepared(audio, rms, ref_len, tokens, duration, spec.noise_index)
 
     @torch.inference_mode()
-    def generate_device(self, specs: list[UtteranceSpec], nfe_step=nfe_step, cfg_strength=cfg_strength,
-                        sway_sampling_coef=sway_sampling_coef, speed=speed, fix_duration=fix_duration,
-                        y0: list | None = None):
-        """Host inputs -> device waveforms.  Returns (wav_flat fp32 on device, offsets, frames, ws, layout, preps)."""
+    def stage(self, specs: list[UtteranceSpec], nfe_step=nfe_step, sway_sampling_coef=sway_sampling_coef, speed=speed,
+              fix_duration=fix_duration, y0: list | None = None) -> "Staged":
+        """Host side + H2D of one request batch: tokenise, duration rule, prompt RMS, pinned copies of prompt audio /
+        noise / tables, prompt mel on the device.  After this the batch is resident in HBM."""
         from .synthetic import initial_noise
         model, dev = self.model, self.device
         preps = [self._prep(s, speed, fix_duration) for s in specs]
-        # H2D: prompt audio (pinned), grouped by length so the STFT batches
         mels: list = [None] * len(preps)
         by_len: dict[int, list[int]] = {}
         for i, p in enumerate(preps):
             by_len.setdefault(p.audio.shape[-1], []).append(i)
         h2d = 0
-        for nw, idx in by_len.items():
+        for nw, idx in by_len.items():                                            # same-length prompts share one STFT
             host = torch.stack([preps[i].audio[0] for i in idx]).pin_memory()
             h2d += host.numel() * 4
             m = mel_spectrogram(host.to(dev, non_blocking=True)).permute(0, 2, 1)
@@ -302,21 +318,34 @@ class Synthesizer:
             lens_i = max(int(tid.numel()), m.shape[0])
             n = min(max(lens_i + 1, p.duration), 4096)
             utts.append(UtteranceInput(cond=m, text_ids=tid, n=n, cond_len=lens_i, y0=nz))
-        ws, layout = model.engine.sample_packed(utts, steps=nfe_step, cfg_strength=cfg_strength,
-                                                sway_sampling_coef=sway_sampling_coef)
+        ws, layout = model.engine.stage(utts, nfe_step, sway_sampling_coef)
         h2d += ws.h2d_bytes
-        # vocoder on the generated frames only (utils_infer.py:468-472)
-        veng = self.vocoder.engine
+        veng = self.vocoder.engine                                                # vocoder rows = generated frames only
         frames = [n - p.ref_len for n, p in zip(layout.lengths, preps)]
         starts, Rv, pos, offs, tot = veng.plan(frames)
         src_rows = torch.full((Rv,), -1, dtype=torch.int32)
         for s, T_, ls, p in zip(starts, frames, layout.starts, preps):
             src_rows[s:s + T_] = torch.arange(ls + p.ref_len, ls + p.ref_len + T_, dtype=torch.int32)
         gains = torch.tensor([p.rms / target_rms if p.rms < target_rms else 1.0 for p in preps], dtype=torch.float32)
-        h2d += src_rows.numel() * 4 + pos.numel() * 4 + gains.numel() * 4
-        wav = veng.decode_rows(ws.x, src_rows.to(dev), pos.to(dev), starts, frames, offs, tot, gains.to(dev))  # :475-476 fused
+        seg = torch.tensor([[s, T_, o, 0] for s, T_, o in zip(starts, frames, offs)], dtype=torch.int32)
+        h2d += (src_rows.numel() + pos.numel() + gains.numel() + seg.numel()) * 4
+        st = Staged(ws, layout, preps, frames, offs, tot, src_rows.to(dev), pos.to(dev), gains.to(dev), seg.to(dev),
+                    nfe_step, h2d)
         self.last_h2d_bytes = h2d
-        return wav, offs, frames, tot, ws, layout, preps
+        return st
+
+    @torch.inference_mode()
+    def run(self, st: "Staged", cfg_strength=cfg_strength) -> torch.Tensor:
+        """Device-resident hot path: sampler + vocoder on a staged batch -> flat fp32 waveform buffer on the device."""
+        self.model.engine.compute(st.ws, st.nfe_step, cfg_strength)
+        return self.vocoder.engine.decode_rows(st.ws.x, st.src_rows, st.vpos, st.seg, st.frames, st.total, st.gains)
+
+    def generate_device(self, specs: list[UtteranceSpec], nfe_step=nfe_step, cfg_strength=cfg_strength,
+                        sway_sampling_coef=sway_sampling_coef, speed=speed, fix_duration=fix_duration,
+                        y0: list | None = None):
+        st = self.stage(specs, nfe_step, sway_sampling_coef, speed, fix_duration, y0)
+        wav = self.run(st, cfg_strength)
+        return wav, st.offs, st.frames, st.total, st.ws, st.layout, st.preps
 
     @torch.inference_mode()
     def generate(self, specs: list[UtteranceSpec], nfe_step=nfe_step, cfg_strength=cfg_strength,

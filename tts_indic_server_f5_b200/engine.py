@@ -20,7 +20,7 @@ from dataclasses import dataclass
 
 import torch
 
-from . import ops
+from . import _lib, ops
 from .layout import PackedLayout, build_layout
 from .weights import DiTConfig
 
@@ -140,6 +140,7 @@ class Workspace:
         z = lambda r, c, dt: torch.zeros(r, c, device=device, dtype=dt)  # noqa: E731
         self.R = R
         self.x = z(R, MELP, F32)               # ODE state
+        self.x0 = z(R, MELP, F32)              # initial noise y0 (kept so a staged batch can be re-run)
         self.cond = z(R, MELP, F32)            # step_cond
         self.xb = z(2 * R, MELP, BF16)         # bf16 copy of x for both CFG halves
         self.pred = z(2 * R, MELP, F32)
@@ -219,7 +220,7 @@ class F5Engine:
                 h_cond[s:s + n, :mel] = torch.where(mask[:, None], c, torch.zeros_like(c))
             nt = min(u.text_ids.numel(), n)                      # dit.py:48-51: +1, truncate to n, filler 0
             h_ids[s:s + nt] = (u.text_ids[:nt] + 1).to(I32)
-        ws.x.copy_(h_x, non_blocking=True)
+        ws.x0.copy_(h_x, non_blocking=True)
         ws.cond.copy_(h_cond, non_blocking=True)
         for s, f, c in dev_conds:
             ws.cond[s:s + f, :mel].copy_(c[:f])
@@ -313,26 +314,40 @@ class F5Engine:
             self.step(ws, 0, cfg_strength)            # eager warm-up of every kernel variant (sets func attributes) ...
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
+            n0 = _lib.launch_count
             with torch.cuda.graph(g):                 # capture records, it does not execute
                 for s in range(steps):
                     self.step(ws, s, cfg_strength)
+            self._graph_launches = _lib.launch_count - n0
+            _lib.launch_count = n0
             ws.x.copy_(x_saved)                       # ... then restore the state the warm-up step advanced
             ops.pack_bf16(ws.x, ws.xb, 0, self.cfg.mel_dim, MELP, row_pos=ws.row_pos, M=ws.R)
             ops.pack_bf16(ws.x, ws.xb[ws.R:], 0, self.cfg.mel_dim, MELP, row_pos=ws.row_pos, M=ws.R)
             self._graphs = {key: g}                   # one live graph (its node arguments point into this workspace)
         g.replay()
+        _lib.launch_count += self._graph_launches
 
     # ------------------------------------------------------------------------------------------ public
-    def sample_packed(self, utts: list[UtteranceInput], steps: int = 32, cfg_strength: float = 2.0,
-                      sway_sampling_coef: float | None = -1.0) -> tuple[Workspace, PackedLayout]:
-        """Run the sampler for a batch; the result stays on the device in `ws.x` (rows per `layout`)."""
-        if cfg_strength < 1e-5:
-            raise NotImplementedError("cfg_strength < 1e-5 (single-branch sampling, cfm.py:170-171) is not on the served path")
+    def stage(self, utts: list[UtteranceInput], steps: int = 32, sway_sampling_coef: float | None = -1.0):
+        """Host -> device: build the packed layout and copy this batch's inputs (pinned H2D).  No arithmetic."""
         layout = build_layout([u.n for u in utts])
         ws = self.upload(utts, layout, steps, sway_sampling_coef)
+        return ws, layout
+
+    def compute(self, ws: Workspace, steps: int = 32, cfg_strength: float = 2.0) -> None:
+        """Device-resident hot path on a staged batch: hoisted work, the Euler loop, prompt re-insert (cfm.py:160-204)."""
+        if cfg_strength < 1e-5:
+            raise NotImplementedError("cfg_strength < 1e-5 (single-branch sampling, cfm.py:170-171) is not on the served path")
+        ws.x.copy_(ws.x0)
         self.hoist(ws, steps)
         self.run_steps(ws, steps, cfg_strength)
         ops.where_rows(ws.x, ws.cond, ws.cond_flag, self.cfg.mel_dim)        # cfm.py:204
+
+    def sample_packed(self, utts: list[UtteranceInput], steps: int = 32, cfg_strength: float = 2.0,
+                      sway_sampling_coef: float | None = -1.0) -> tuple[Workspace, PackedLayout]:
+        """Run the sampler for a batch; the result stays on the device in `ws.x` (rows per `layout`)."""
+        ws, layout = self.stage(utts, steps, sway_sampling_coef)
+        self.compute(ws, steps, cfg_strength)
         return ws, layout
 
     def forward_flow(self, utts: list[UtteranceInput], t: float) -> list[torch.Tensor]:
@@ -340,6 +355,7 @@ class F5Engine:
         layout = build_layout([u.n for u in utts])
         ws = self.upload(utts, layout, 1, None)
         ws.tgrid[0] = t
+        ws.x.copy_(ws.x0)
         self.hoist(ws, 1)
         graphs, self.use_graphs = self.use_graphs, False
         ws.dts.zero_()

@@ -83,10 +83,11 @@ class VocosEngine:
             tot += 256 * max(T - 1, 0)
         return starts, Rv, pos, offs, tot
 
-    def decode_rows(self, src: torch.Tensor, src_rows: torch.Tensor, row_pos: torch.Tensor, starts: list[int],
-                    frames: list[int], offs: list[int], total: int, gains: torch.Tensor | None = None) -> torch.Tensor:
-        """src fp32 [*, >=n_mels] device mel rows; src_rows int32 [Rv] maps vocoder rows to src rows (-1 = zero row).
-        Returns the flat fp32 waveform buffer (utterance i at offs[i], 256*(frames[i]-1) samples)."""
+    def decode_rows(self, src: torch.Tensor, src_rows: torch.Tensor, row_pos: torch.Tensor, seg: torch.Tensor,
+                    frames: list[int], total: int, gains: torch.Tensor | None = None) -> torch.Tensor:
+        """src fp32 [*, >=n_mels] device mel rows; src_rows int32 [Rv] maps vocoder rows to src rows (-1 = zero row);
+        seg int32 [S,4] = {row0, frames, wav_offset, 0} on the device.  Returns the flat fp32 waveform buffer
+        (utterance i at its offset, 256*(frames[i]-1) samples).  Device-resident: no host copies."""
         cfg, Rv = self.cfg, src_rows.shape[0]
         b = self._buffers(Rv)
         C = cfg.dim
@@ -101,7 +102,6 @@ class VocosEngine:
         ops.layernorm_mod(b["v"], b["hb"], self.fin_w, self.fin_b, 0.0)
         ops.gemm(b["hb"], self.head_w, mode=ops.F5_EPI_STORE_F32, bias=self.head_b, out=b["spec"], block_n=128)
         wav = torch.empty(max(total, 1), device=self.device, dtype=F32)
-        seg = torch.tensor([[s, T, o, 0] for s, T, o in zip(starts, frames, offs)], dtype=I32).to(self.device)
         ops.istft(b["spec"], self.window, b["frames"], seg, 256 * max(max(frames) - 1, 1), wav, gains)
         return wav
 
@@ -115,5 +115,6 @@ class VocosEngine:
         src_rows = torch.full((Rv,), -1, dtype=I32)
         for i, s in enumerate(starts):
             src_rows[s:s + T] = torch.arange(i * T, (i + 1) * T, dtype=I32)
-        wav = self.decode_rows(src, src_rows.to(self.device), pos.to(self.device), starts, [T] * B, offs, tot)
+        seg = torch.tensor([[s, T, o, 0] for s, o in zip(starts, offs)], dtype=I32).to(self.device)
+        wav = self.decode_rows(src, src_rows.to(self.device), pos.to(self.device), seg, [T] * B, tot)
         return wav[:tot].view(B, 256 * (T - 1))
