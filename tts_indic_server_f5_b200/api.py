@@ -110,7 +110,7 @@ class CFM:
             utts.append(UtteranceInput(cond=cond[i], text_ids=ids, n=n, cond_len=int(lens_t[i]), y0=noise, edit_mask=em))
         return utts
 
-    @torch.no_grad()
+    @torch.inference_mode()
     def sample(self, cond, text, duration, *, lens=None, steps=32, cfg_strength=1.0, sway_sampling_coef=None, seed=None,
                max_duration=4096, vocoder=None, no_ref_audio=False, duplicate_test=False, t_inter=0.1, edit_mask=None,
                y0=None):

@@ -328,12 +328,14 @@ class F5Engine:
         _lib.launch_count += self._graph_launches
 
     # ------------------------------------------------------------------------------------------ public
+    @torch.inference_mode()
     def stage(self, utts: list[UtteranceInput], steps: int = 32, sway_sampling_coef: float | None = -1.0):
         """Host -> device: build the packed layout and copy this batch's inputs (pinned H2D).  No arithmetic."""
         layout = build_layout([u.n for u in utts])
         ws = self.upload(utts, layout, steps, sway_sampling_coef)
         return ws, layout
 
+    @torch.inference_mode()
     def compute(self, ws: Workspace, steps: int = 32, cfg_strength: float = 2.0) -> None:
         """Device-resident hot path on a staged batch: hoisted work, the Euler loop, prompt re-insert (cfm.py:160-204)."""
         if cfg_strength < 1e-5:
@@ -350,6 +352,7 @@ class F5Engine:
         self.compute(ws, steps, cfg_strength)
         return ws, layout
 
+    @torch.inference_mode()
     def forward_flow(self, utts: list[UtteranceInput], t: float) -> list[torch.Tensor]:
         """One CFG velocity evaluation pair at time t (test hook): returns per utterance [2, n, mel] (cond, null)."""
         layout = build_layout([u.n for u in utts])

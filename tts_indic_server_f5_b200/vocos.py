@@ -83,6 +83,7 @@ class VocosEngine:
             tot += 256 * max(T - 1, 0)
         return starts, Rv, pos, offs, tot
 
+    @torch.inference_mode()
     def decode_rows(self, src: torch.Tensor, src_rows: torch.Tensor, row_pos: torch.Tensor, seg: torch.Tensor,
                     frames: list[int], total: int, gains: torch.Tensor | None = None) -> torch.Tensor:
         """src fp32 [*, >=n_mels] device mel rows; src_rows int32 [Rv] maps vocoder rows to src rows (-1 = zero row);
