@@ -154,58 +154,84 @@ attn_d64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnParams p
     const int row = quarter * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
     float m_run = -INFINITY, l_run = 0.f;
+    const float2 sc2 = make_float2(p.scale_log2, p.scale_log2);
     for (int j = 0; j < nkv; ++j) {
       const int kv_valid = min(ATT_BN, kv_len - j * ATT_BN);
+      const bool full = kv_valid == ATT_BN;           // only the last tile of an utterance needs key masking
       mbar_wait(s_full, j & 1);
       tc_fence_after();
-      // pass 1: row max
+      // pass 1: row max of the raw scores (S stays in TMEM; re-reading it is cheaper than holding 128 registers)
       float mx = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < ATT_BN / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(tmem_S + lane_off + c * 32, r);
-        tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (c * 32 + i < kv_valid) mx = fmaxf(mx, __uint_as_float(r[i]));
+      for (int h = 0; h < 2; ++h) {
+        uint32_t r0[32], r1[32];
+        tmem_ld_32x32b_x32(tmem_S + lane_off + h * 64, r0);
+        tmem_ld_32x32b_x32(tmem_S + lane_off + h * 64 + 32, r1);
+        tmem_ld_wait();
+        if (full) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaxf(__uint_as_float(r0[i]), __uint_as_float(r1[i])));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            if (h * 64 + i < kv_valid) mx = fmaxf(mx, __uint_as_float(r0[i]));
+            if (h * 64 + 32 + i < kv_valid) mx = fmaxf(mx, __uint_as_float(r1[i]));
+          }
+        }
       }
+      // lazy rescale: keep a stale running max while it is within 2^8 of the true one (p <= 256 is harmless in bf16/fp32);
+      // O and l are only rescaled when the max really moved.  The first tile always "grows" (m_run = -inf, alpha = 0).
       const float m_new = fmaxf(m_run, mx * p.scale_log2);
-      const float alpha = exp2f(m_run - m_new);   // 0 on the first tile (m_run = -inf)
+      const bool grow = (m_new - m_run) > 8.f;
+      const bool any_grow = __any_sync(0xffffffffu, grow);
+      float alpha = 1.f;
+      if (grow) {
+        alpha = fast_ex2(m_run - m_new);
+        m_run = m_new;
+      }
       // previous PV must be complete before P is overwritten / O is rescaled
       if (j > 0) {
         mbar_wait(o_full, (j - 1) & 1);
         tc_fence_after();
       }
       // pass 2: p = exp2(s*scale - m), row sum, bf16 P -> swizzled smem
-      float lsum = 0.f;
-#pragma unroll 1
+      const float2 nm2 = make_float2(-m_run, -m_run);
+      float2 ls2 = make_float2(0.f, 0.f);
+#pragma unroll
       for (int c = 0; c < ATT_BN / 32; ++c) {
         uint32_t r[32];
         tmem_ld_32x32b_x32(tmem_S + lane_off + c * 32, r);
         tmem_ld_wait();
-        float pv[32];
+        uint32_t pk[16];
+        if (full) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float s = __uint_as_float(r[i]);
-          const float e = (c * 32 + i < kv_valid) ? exp2f(fmaf(s, p.scale_log2, -m_new)) : 0.f;
-          pv[i] = e;
-          lsum += e;
+          for (int i = 0; i < 16; ++i) {
+            float2 t = ffma2(make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), sc2, nm2);
+            t.x = fast_ex2(t.x);
+            t.y = fast_ex2(t.y);
+            ls2 = fadd2(ls2, t);
+            pk[i] = pack_bf16x2(t.x, t.y);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int k0 = c * 32 + 2 * i;
+            const float e0 = k0 < kv_valid ? fast_ex2(fmaf(__uint_as_float(r[2 * i]), p.scale_log2, -m_run)) : 0.f;
+            const float e1 = k0 + 1 < kv_valid ? fast_ex2(fmaf(__uint_as_float(r[2 * i + 1]), p.scale_log2, -m_run)) : 0.f;
+            ls2.x += e0;
+            ls2.y += e1;
+            pk[i] = pack_bf16x2(e0, e1);
+          }
         }
         uint8_t* blk = sP + (c >> 1) * ATT_TILE_BYTES + row * 128;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int chunk = (c & 1) * 4 + q;
-          uint4 w;
-          w.x = pack_bf16x2(pv[q * 8 + 0], pv[q * 8 + 1]);
-          w.y = pack_bf16x2(pv[q * 8 + 2], pv[q * 8 + 3]);
-          w.z = pack_bf16x2(pv[q * 8 + 4], pv[q * 8 + 5]);
-          w.w = pack_bf16x2(pv[q * 8 + 6], pv[q * 8 + 7]);
-          *reinterpret_cast<uint4*>(blk + ((chunk ^ (row & 7)) << 4)) = w;
+          *reinterpret_cast<uint4*>(blk + ((chunk ^ (row & 7)) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
         }
       }
-      l_run = l_run * alpha + lsum;
-      m_run = m_new;
-      if (j > 0 && __any_sync(0xffffffffu, alpha != 1.f)) {
+      l_run = l_run * alpha + (ls2.x + ls2.y);
+      if (j > 0 && any_grow) {
 #pragma unroll 1
         for (int c = 0; c < ATT_D / 32; ++c) {
           uint32_t r[32];

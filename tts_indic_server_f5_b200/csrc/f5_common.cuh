@@ -179,6 +179,45 @@ __device__ __forceinline__ float mish(float x) {
   float sp = (x > 20.f) ? x : log1pf(expf(x));
   return x * tanhf(sp);
 }
+// MUFU-based fast forms used in GEMM epilogues (results are rounded to bf16 or added to an fp32 stream; ex2.approx has
+// 2^-22 relative error, rcp.approx 1 ulp — far below bf16's 2^-9).
+__device__ __forceinline__ float fast_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float fast_rcp(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// 0.5 x (1 + tanh(u)) == x * sigmoid(2u) == x / (1 + exp(-2u)),  u = sqrt(2/pi) (x + 0.044715 x^3)
+__device__ __forceinline__ float gelu_tanh_fast(float x) {
+  const float c0 = -2.f * 0.7978845608028654f * 1.4426950408889634f;   // -2 sqrt(2/pi) log2(e)
+  const float t = c0 * (x + 0.044715f * x * x * x);
+  return x * fast_rcp(1.f + fast_ex2(t));
+}
+// x tanh(log(1+e^x)) == x n / (n + 2),  n = e^x (e^x + 2)
+__device__ __forceinline__ float mish_fast(float x) {
+  const float e = fast_ex2(fminf(x, 20.f) * 1.4426950408889634f);
+  const float n = e * (e + 2.f);
+  return x * n * fast_rcp(n + 2.f);
+}
+// packed 2-wide fp32 (sm_100: FFMA2 / FADD2 halve the issue slots of the softmax inner loop)
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;"
+      : "=l"(reinterpret_cast<uint64_t&>(d))
+      : "l"(reinterpret_cast<const uint64_t&>(a)), "l"(reinterpret_cast<const uint64_t&>(b)), "l"(reinterpret_cast<const uint64_t&>(c)));
+  return d;
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+  float2 d;
+  asm("add.f32x2 %0, %1, %2;"
+      : "=l"(reinterpret_cast<uint64_t&>(d))
+      : "l"(reinterpret_cast<const uint64_t&>(a)), "l"(reinterpret_cast<const uint64_t&>(b)));
+  return d;
+}
 __device__ __forceinline__ float silu(float x) { return x / (1.f + expf(-x)); }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {

@@ -26,7 +26,8 @@ struct GemmCfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = BLOCK_N == 256 ? 4 : (BLOCK_N == 128 ? 6 : 8);
   static constexpr int TMEM_COLS = 2 * BLOCK_N;  // 512 / 256 / 128: powers of two >= 32
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int EPI_STAGE_BYTES = 4 * 4096;   // one 32-row x 128-B staging tile per epilogue warp
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 struct GemmParams {
@@ -45,9 +46,9 @@ struct GemmParams {
 
 __device__ __forceinline__ float apply_act(float v, int act) {
   switch (act) {
-    case F5_ACT_GELU_TANH: return gelu_tanh(v);
+    case F5_ACT_GELU_TANH: return gelu_tanh_fast(v);
     case F5_ACT_GELU_ERF: return gelu_erf(v);
-    case F5_ACT_MISH: return mish(v);
+    case F5_ACT_MISH: return mish_fast(v);
     default: return v;
   }
 }
@@ -59,7 +60,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   using Cfg = GemmCfg<BLOCK_N>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint8_t* stage_base = smem + Cfg::STAGES * Cfg::STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stage_base + Cfg::EPI_STAGE_BYTES);
   uint64_t* empty_bar = full_bar + Cfg::STAGES;
   uint64_t* tmem_full = empty_bar + Cfg::STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
@@ -144,114 +146,149 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
   } else {
     // ------------------------------------------------------------ epilogue (warps 2..5)
+    // TMEM -> registers (thread = row) -> bias / activation / RoPE / gate -> per-warp 4 KB smem staging tile (32 rows x
+    // 128 B, 16-B chunks XOR-swizzled by row) -> read back with 8 lanes per row so that every global access is a full,
+    // coalesced 128-B line (bf16 stores, fp32 stores, and the fp32 residual read-modify-write).
     const int quarter = warp & 3;           // TMEM lane quarter this warp may access
+    uint8_t* stg = stage_base + (warp - 2) * 4096;
+    const int rd_row = lane >> 3, rd_chunk = lane & 7;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m0 = (tile / p.num_n_tiles) * BLOCK_M;
       const int n0 = (tile % p.num_n_tiles) * BLOCK_N;
-      const int m = m0 + quarter * 32 + lane;
-      const bool row_ok = m < p.M;
+      const int mw = m0 + quarter * 32;     // first row of this warp
+      const int m = mw + lane;
       int pos = 0;
-      if (p.row_pos != nullptr && row_ok) pos = p.row_pos[m];
+      if (p.row_pos != nullptr && m < p.M) pos = p.row_pos[m];
       const bool zero_row = p.mask_rows && pos < 0;
       const bool rope_tile = p.rope != nullptr && (n0 % p.rope_period) == 0 && (n0 / p.rope_period) < p.rope_tiles;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BLOCK_N;
+      uint8_t* wr = stg + lane * 128;
 
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
+      if (p.mode == F5_EPI_STORE_BF16) {
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BLOCK_N + c * 32, r);
-        tmem_ld_wait();
-        const int nc = n0 + c * 32;
-        if (row_ok && nc < p.N) {
-          float v[32];
+        for (int u = 0; u < BLOCK_N / 64; ++u) {          // 64 output columns = 128 B of bf16 per row
+          uint32_t r0[32], r1[32];
+          tmem_ld_32x32b_x32(taddr + u * 64, r0);
+          tmem_ld_32x32b_x32(taddr + u * 64 + 32, r1);
+          tmem_ld_wait();
+          const int nc = n0 + u * 64;
+          if (nc < p.N) {                                  // warp-uniform
+            float v[64];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          if (p.bias != nullptr) {
+            for (int j = 0; j < 32; ++j) { v[j] = __uint_as_float(r0[j]); v[32 + j] = __uint_as_float(r1[j]); }
+            if (p.bias != nullptr) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              if (nc + j < p.N) {
-                const float4 b4 = *reinterpret_cast<const float4*>(p.bias + nc + j);
-                v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+              for (int j = 0; j < 64; j += 4) {
+                if (nc + j < p.N) {
+                  const float4 b4 = *reinterpret_cast<const float4*>(p.bias + nc + j);
+                  v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+                }
               }
             }
-          }
-          if (p.act != F5_ACT_NONE) {
+            if (p.act != F5_ACT_NONE) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act);
-          }
-          if (p.mode == F5_EPI_STORE_BF16) {
-            if (rope_tile && c < 2 && pos >= 0) {
+              for (int j = 0; j < 64; ++j) v[j] = apply_act(v[j], p.act);
+            }
+            if (rope_tile && u == 0 && pos >= 0) {
               // interleaved-pair rotation of head 0 (x-transformers apply_rotary_pos_emb; model/modules.py:418-419)
-              const float2* cs = reinterpret_cast<const float2*>(p.rope) + static_cast<size_t>(pos) * 32 + c * 16;
+              const float2* cs = reinterpret_cast<const float2*>(p.rope) + static_cast<size_t>(pos) * 32;
 #pragma unroll
-              for (int i = 0; i < 16; ++i) {
+              for (int i = 0; i < 32; ++i) {
                 const float2 t = cs[i];
                 const float x0 = v[2 * i], x1 = v[2 * i + 1];
                 v[2 * i] = x0 * t.x - x1 * t.y;
                 v[2 * i + 1] = x1 * t.x + x0 * t.y;
               }
             }
-            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(m) * p.ldo + nc;
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              if (nc + j < p.N) {
-                uint4 q;
-                if (zero_row) {
-                  q = make_uint4(0, 0, 0, 0);
-                } else {
-                  q.x = pack_bf16x2(v[j], v[j + 1]); q.y = pack_bf16x2(v[j + 2], v[j + 3]);
-                  q.z = pack_bf16x2(v[j + 4], v[j + 5]); q.w = pack_bf16x2(v[j + 6], v[j + 7]);
-                }
-                *reinterpret_cast<uint4*>(o + j) = q;
+            for (int q = 0; q < 8; ++q) {
+              uint4 w = make_uint4(0, 0, 0, 0);
+              if (!zero_row) {
+                w.x = pack_bf16x2(v[8 * q], v[8 * q + 1]); w.y = pack_bf16x2(v[8 * q + 2], v[8 * q + 3]);
+                w.z = pack_bf16x2(v[8 * q + 4], v[8 * q + 5]); w.w = pack_bf16x2(v[8 * q + 6], v[8 * q + 7]);
+              }
+              *reinterpret_cast<uint4*>(wr + ((q ^ (lane & 7)) << 4)) = w;
+            }
+            __syncwarp();
+            const int col = nc + rd_chunk * 8;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int row = i * 4 + rd_row;
+              if (mw + row < p.M && col < p.N) {
+                const uint4 w = *reinterpret_cast<const uint4*>(stg + row * 128 + ((rd_chunk ^ (row & 7)) << 4));
+                *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(mw + row) * p.ldo + col) = w;
               }
             }
-          } else if (p.mode == F5_EPI_STORE_F32) {
-            if (p.addend != nullptr) {
-              const float* a = p.addend + static_cast<size_t>(m) * p.ld_add + nc;
+            __syncwarp();
+          }
+        }
+      } else {
+#pragma unroll 1
+        for (int u = 0; u < BLOCK_N / 32; ++u) {          // 32 output columns = 128 B of fp32 per row
+          uint32_t r0[32];
+          tmem_ld_32x32b_x32(taddr + u * 32, r0);
+          tmem_ld_wait();
+          const int nc = n0 + u * 32;
+          if (nc < p.N) {
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r0[j]);
+            if (p.bias != nullptr) {
 #pragma unroll
               for (int j = 0; j < 32; j += 4) {
                 if (nc + j < p.N) {
-                  const float4 a4 = *reinterpret_cast<const float4*>(a + j);
-                  v[j] += a4.x; v[j + 1] += a4.y; v[j + 2] += a4.z; v[j + 3] += a4.w;
+                  const float4 b4 = *reinterpret_cast<const float4*>(p.bias + nc + j);
+                  v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
                 }
               }
             }
-            float* o = reinterpret_cast<float*>(p.out) + static_cast<size_t>(m) * p.ldo + nc;
+            if (p.act != F5_ACT_NONE) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              if (nc + j < p.N) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+              for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act);
             }
-            if (p.out2 != nullptr) {
-              __nv_bfloat16* o2 = reinterpret_cast<__nv_bfloat16*>(p.out2) + static_cast<size_t>(m) * p.ldo2 + nc;
+            if (p.mode == F5_EPI_RESID_F32 && p.gate != nullptr) {
 #pragma unroll
-              for (int j = 0; j < 32; j += 8) {
+              for (int j = 0; j < 32; j += 4) {
                 if (nc + j < p.N) {
-                  uint4 q;
-                  if (zero_row) {
-                    q = make_uint4(0, 0, 0, 0);
-                  } else {
-                    q.x = pack_bf16x2(v[j], v[j + 1]); q.y = pack_bf16x2(v[j + 2], v[j + 3]);
-                    q.z = pack_bf16x2(v[j + 4], v[j + 5]); q.w = pack_bf16x2(v[j + 6], v[j + 7]);
-                  }
-                  *reinterpret_cast<uint4*>(o2 + j) = q;
+                  const float4 g4 = *reinterpret_cast<const float4*>(p.gate + nc + j);
+                  v[j] *= g4.x; v[j + 1] *= g4.y; v[j + 2] *= g4.z; v[j + 3] *= g4.w;
                 }
               }
             }
-          } else {  // F5_EPI_RESID_F32
-            float* x = p.resid + static_cast<size_t>(m) * p.ldr + nc;
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              if (nc + j < p.N) {
-                float4 x4 = *reinterpret_cast<const float4*>(x + j);
-                float4 g4 = make_float4(1.f, 1.f, 1.f, 1.f);
-                if (p.gate != nullptr) g4 = *reinterpret_cast<const float4*>(p.gate + nc + j);
-                x4.x += g4.x * v[j]; x4.y += g4.y * v[j + 1]; x4.z += g4.z * v[j + 2]; x4.w += g4.w * v[j + 3];
-                *reinterpret_cast<float4*>(x + j) = x4;
+            for (int q = 0; q < 8; ++q)
+              *reinterpret_cast<float4*>(wr + ((q ^ (lane & 7)) << 4)) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            __syncwarp();
+            const int col = nc + rd_chunk * 4;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int row = i * 4 + rd_row;
+              const int mr = mw + row;
+              if (mr < p.M && col < p.N) {
+                float4 y = *reinterpret_cast<const float4*>(stg + row * 128 + ((rd_chunk ^ (row & 7)) << 4));
+                if (p.mode == F5_EPI_RESID_F32) {
+                  float4* x = reinterpret_cast<float4*>(p.resid + static_cast<size_t>(mr) * p.ldr + col);
+                  const float4 x4 = *x;
+                  *x = make_float4(x4.x + y.x, x4.y + y.y, x4.z + y.z, x4.w + y.w);
+                } else {
+                  if (p.addend != nullptr) {
+                    const float4 a4 = *reinterpret_cast<const float4*>(p.addend + static_cast<size_t>(mr) * p.ld_add + col);
+                    y.x += a4.x; y.y += a4.y; y.z += a4.z; y.w += a4.w;
+                  }
+                  *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + static_cast<size_t>(mr) * p.ldo + col) = y;
+                  if (p.out2 != nullptr) {
+                    const bool zr = p.mask_rows && p.row_pos[mr] < 0;
+                    const uint2 w = zr ? make_uint2(0, 0) : make_uint2(pack_bf16x2(y.x, y.y), pack_bf16x2(y.z, y.w));
+                    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out2) + static_cast<size_t>(mr) * p.ldo2 + col) = w;
+                  }
+                }
               }
             }
+            __syncwarp();
           }
         }
       }
