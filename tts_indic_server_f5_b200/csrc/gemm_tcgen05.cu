@@ -27,7 +27,8 @@ struct GemmCfg {
   static constexpr int STAGES = BLOCK_N == 256 ? 4 : (BLOCK_N == 128 ? 6 : 8);
   static constexpr int TMEM_COLS = 2 * BLOCK_N;  // 512 / 256 / 128: powers of two >= 32
   static constexpr int EPI_STAGE_BYTES = 4 * 4096;   // one 32-row x 128-B staging tile per epilogue warp
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int EPI_BIAS_BYTES = 4 * BLOCK_N * 4;   // per-warp copy of the tile's bias slice
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGE_BYTES + EPI_BIAS_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 struct GemmParams {
@@ -44,16 +45,17 @@ struct GemmParams {
   const float* rope; int rope_period, rope_tiles;
 };
 
-__device__ __forceinline__ float apply_act(float v, int act) {
-  switch (act) {
-    case F5_ACT_GELU_TANH: return gelu_tanh_fast(v);
-    case F5_ACT_GELU_ERF: return gelu_erf(v);
-    case F5_ACT_MISH: return mish_fast(v);
-    default: return v;
-  }
+// The activation is a compile-time parameter: a runtime switch would inline all three bodies into every unrolled
+// element of the epilogue (tens of KB of straight-line code per warp -> instruction-fetch bound with one warp per scheduler).
+template <int ACT>
+__device__ __forceinline__ float apply_act(float v) {
+  if constexpr (ACT == F5_ACT_GELU_TANH) return gelu_tanh_fast(v);
+  else if constexpr (ACT == F5_ACT_GELU_ERF) return gelu_erf(v);
+  else if constexpr (ACT == F5_ACT_MISH) return mish_fast(v);
+  else return v;
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, int ACT>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const GemmParams p) {
@@ -61,7 +63,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* stage_base = smem + Cfg::STAGES * Cfg::STAGE_BYTES;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stage_base + Cfg::EPI_STAGE_BYTES);
+  float* bias_base = reinterpret_cast<float*>(stage_base + Cfg::EPI_STAGE_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stage_base + Cfg::EPI_STAGE_BYTES + Cfg::EPI_BIAS_BYTES);
   uint64_t* empty_bar = full_bar + Cfg::STAGES;
   uint64_t* tmem_full = empty_bar + Cfg::STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
@@ -146,31 +149,64 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
   } else {
     // ------------------------------------------------------------ epilogue (warps 2..5)
-    // TMEM -> registers (thread = row) -> bias / activation / RoPE / gate -> per-warp 4 KB smem staging tile (32 rows x
-    // 128 B, 16-B chunks XOR-swizzled by row) -> read back with 8 lanes per row so that every global access is a full,
-    // coalesced 128-B line (bf16 stores, fp32 stores, and the fp32 residual read-modify-write).
+    // Per 32-column unit: TMEM -> registers (thread = row) -> raw fp32 into a per-warp 4 KB staging tile (32 rows x 128 B,
+    // 16-B chunks XOR-swizzled by row) -> read back with 8 lanes per row, so every global access (bf16/fp32 stores, the
+    // fp32 residual read-modify-write, addend, bias, gate, RoPE table) is coalesced and each lane needs ONE bias/gate
+    // float4 per unit.  All side loads are issued a unit ahead: with ~210 KB of smem carved out the L1 is tiny, so a
+    // dependent global load on the critical path costs an L2 round trip.
     const int quarter = warp & 3;           // TMEM lane quarter this warp may access
     uint8_t* stg = stage_base + (warp - 2) * 4096;
     const int rd_row = lane >> 3, rd_chunk = lane & 7;
+    constexpr int UNITS = BLOCK_N / 32;
+    const float* side = p.mode == F5_EPI_RESID_F32 ? p.resid : (p.mode == F5_EPI_STORE_F32 ? p.addend : nullptr);
+    const long long side_ld = p.mode == F5_EPI_RESID_F32 ? p.ldr : p.ld_add;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m0 = (tile / p.num_n_tiles) * BLOCK_M;
       const int n0 = (tile % p.num_n_tiles) * BLOCK_N;
       const int mw = m0 + quarter * 32;     // first row of this warp
-      const int m = mw + lane;
-      int pos = 0;
-      if (p.row_pos != nullptr && m < p.M) pos = p.row_pos[m];
-      const bool zero_row = p.mask_rows && pos < 0;
       const bool rope_tile = p.rope != nullptr && (n0 % p.rope_period) == 0 && (n0 / p.rope_period) < p.rope_tiles;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BLOCK_N;
       uint8_t* wr = stg + lane * 128;
-
-      mbar_wait(&tmem_full[acc], acc_phase);
-      tc_fence_after();
+      int pos8[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int mr = mw + i * 4 + rd_row;
+        pos8[i] = (p.row_pos != nullptr && mr < p.M) ? p.row_pos[mr] : 0;
+      }
+      float4 nxt[8], nb, ng;
+      auto prefetch = [&](int u) {
+        const int col = n0 + u * 32 + rd_chunk * 4;
+        const bool cok = col < p.N;
+        nb = (p.bias != nullptr && cok) ? *reinterpret_cast<const float4*>(p.bias + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+        ng = (p.gate != nullptr && cok) ? *reinterpret_cast<const float4*>(p.gate + col) : make_float4(1.f, 1.f, 1.f, 1.f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int mr = mw + i * 4 + rd_row;
+          nxt[i] = (side != nullptr && mr < p.M && cok)
+                       ? *reinterpret_cast<const float4*>(side + static_cast<size_t>(mr) * side_ld + col)
+                       : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      };
       if (p.mode == F5_EPI_STORE_BF16) {
+        // bf16 outputs: 64-column units (one full 128-B line per row), math in the thread = row layout, the tile's bias slice
+        // served from a per-warp smem copy (fetched before the accumulator wait).
+        float* bias_s = bias_base + (warp - 2) * BLOCK_N;
+#pragma unroll
+        for (int c = lane * 4; c < BLOCK_N; c += 128) {
+          const float4 b = (p.bias != nullptr && n0 + c < p.N) ? *reinterpret_cast<const float4*>(p.bias + n0 + c)
+                                                               : make_float4(0.f, 0.f, 0.f, 0.f);
+          *reinterpret_cast<float4*>(bias_s + c) = b;
+        }
+        const int m = mw + lane;
+        const int pos = (p.row_pos != nullptr && m < p.M) ? p.row_pos[m] : 0;
+        const bool zero_row = p.mask_rows && pos < 0;
+        __syncwarp();
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tc_fence_after();
 #pragma unroll 1
-        for (int u = 0; u < BLOCK_N / 64; ++u) {          // 64 output columns = 128 B of bf16 per row
+        for (int u = 0; u < BLOCK_N / 64; ++u) {
           uint32_t r0[32], r1[32];
           tmem_ld_32x32b_x32(taddr + u * 64, r0);
           tmem_ld_32x32b_x32(taddr + u * 64 + 32, r1);
@@ -179,29 +215,27 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           if (nc < p.N) {                                  // warp-uniform
             float v[64];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) { v[j] = __uint_as_float(r0[j]); v[32 + j] = __uint_as_float(r1[j]); }
-            if (p.bias != nullptr) {
-#pragma unroll
-              for (int j = 0; j < 64; j += 4) {
-                if (nc + j < p.N) {
-                  const float4 b4 = *reinterpret_cast<const float4*>(p.bias + nc + j);
-                  v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
-                }
-              }
+            for (int j = 0; j < 32; j += 4) {
+              const float4 ba = *reinterpret_cast<const float4*>(bias_s + u * 64 + j);
+              const float4 bb = *reinterpret_cast<const float4*>(bias_s + u * 64 + 32 + j);
+              v[j] = __uint_as_float(r0[j]) + ba.x; v[j + 1] = __uint_as_float(r0[j + 1]) + ba.y;
+              v[j + 2] = __uint_as_float(r0[j + 2]) + ba.z; v[j + 3] = __uint_as_float(r0[j + 3]) + ba.w;
+              v[32 + j] = __uint_as_float(r1[j]) + bb.x; v[33 + j] = __uint_as_float(r1[j + 1]) + bb.y;
+              v[34 + j] = __uint_as_float(r1[j + 2]) + bb.z; v[35 + j] = __uint_as_float(r1[j + 3]) + bb.w;
             }
-            if (p.act != F5_ACT_NONE) {
+            if constexpr (ACT != F5_ACT_NONE) {
 #pragma unroll
-              for (int j = 0; j < 64; ++j) v[j] = apply_act(v[j], p.act);
+              for (int j = 0; j < 64; ++j) v[j] = apply_act<ACT>(v[j]);
             }
             if (rope_tile && u == 0 && pos >= 0) {
               // interleaved-pair rotation of head 0 (x-transformers apply_rotary_pos_emb; model/modules.py:418-419)
-              const float2* cs = reinterpret_cast<const float2*>(p.rope) + static_cast<size_t>(pos) * 32;
+              const float4* cs = reinterpret_cast<const float4*>(p.rope + static_cast<size_t>(pos) * 64);
 #pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                const float2 t = cs[i];
-                const float x0 = v[2 * i], x1 = v[2 * i + 1];
-                v[2 * i] = x0 * t.x - x1 * t.y;
-                v[2 * i + 1] = x1 * t.x + x0 * t.y;
+              for (int i = 0; i < 16; ++i) {
+                const float4 t = cs[i];
+                const float x0 = v[4 * i], x1 = v[4 * i + 1], x2 = v[4 * i + 2], x3 = v[4 * i + 3];
+                v[4 * i] = x0 * t.x - x1 * t.y; v[4 * i + 1] = x1 * t.x + x0 * t.y;
+                v[4 * i + 2] = x2 * t.z - x3 * t.w; v[4 * i + 3] = x3 * t.z + x2 * t.w;
               }
             }
 #pragma unroll
@@ -226,71 +260,56 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             __syncwarp();
           }
         }
-      } else {
+        tc_fence_before();
+        mbar_arrive(&tmem_empty[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        continue;
+      }
+      prefetch(0);                           // in flight while we wait for the accumulator
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
 #pragma unroll 1
-        for (int u = 0; u < BLOCK_N / 32; ++u) {          // 32 output columns = 128 B of fp32 per row
-          uint32_t r0[32];
-          tmem_ld_32x32b_x32(taddr + u * 32, r0);
-          tmem_ld_wait();
-          const int nc = n0 + u * 32;
-          if (nc < p.N) {
-            float v[32];
+      for (int u = 0; u < UNITS; ++u) {
+        float4 cur[8];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r0[j]);
-            if (p.bias != nullptr) {
+        for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
+        const float4 b4 = nb, g4 = ng;
+        if (u + 1 < UNITS) prefetch(u + 1);
+        uint32_t r0[32];
+        tmem_ld_32x32b_x32(taddr + u * 32, r0);
+        tmem_ld_wait();
 #pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                if (nc + j < p.N) {
-                  const float4 b4 = *reinterpret_cast<const float4*>(p.bias + nc + j);
-                  v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+        for (int q = 0; q < 8; ++q)
+          *reinterpret_cast<uint4*>(wr + ((q ^ (lane & 7)) << 4)) = make_uint4(r0[4 * q], r0[4 * q + 1], r0[4 * q + 2], r0[4 * q + 3]);
+        __syncwarp();
+        const int col = n0 + u * 32 + rd_chunk * 4;
+        if (col < p.N) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int row = i * 4 + rd_row;
+            const int mr = mw + row;
+            if (mr < p.M) {
+              float4 y = *reinterpret_cast<const float4*>(stg + row * 128 + ((rd_chunk ^ (row & 7)) << 4));
+              y.x += b4.x; y.y += b4.y; y.z += b4.z; y.w += b4.w;
+              if constexpr (ACT != F5_ACT_NONE) {
+                y.x = apply_act<ACT>(y.x); y.y = apply_act<ACT>(y.y); y.z = apply_act<ACT>(y.z); y.w = apply_act<ACT>(y.w);
+              }
+              if (p.mode == F5_EPI_STORE_F32) {
+                y.x += cur[i].x; y.y += cur[i].y; y.z += cur[i].z; y.w += cur[i].w;
+                *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + static_cast<size_t>(mr) * p.ldo + col) = y;
+                if (p.out2 != nullptr) {
+                  const bool zr = p.mask_rows && pos8[i] < 0;
+                  const uint2 w = zr ? make_uint2(0, 0) : make_uint2(pack_bf16x2(y.x, y.y), pack_bf16x2(y.z, y.w));
+                  *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out2) + static_cast<size_t>(mr) * p.ldo2 + col) = w;
                 }
+              } else {  // F5_EPI_RESID_F32: x += gate * y
+                *reinterpret_cast<float4*>(p.resid + static_cast<size_t>(mr) * p.ldr + col) =
+                    make_float4(fmaf(g4.x, y.x, cur[i].x), fmaf(g4.y, y.y, cur[i].y), fmaf(g4.z, y.z, cur[i].z), fmaf(g4.w, y.w, cur[i].w));
               }
             }
-            if (p.act != F5_ACT_NONE) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act);
-            }
-            if (p.mode == F5_EPI_RESID_F32 && p.gate != nullptr) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                if (nc + j < p.N) {
-                  const float4 g4 = *reinterpret_cast<const float4*>(p.gate + nc + j);
-                  v[j] *= g4.x; v[j + 1] *= g4.y; v[j + 2] *= g4.z; v[j + 3] *= g4.w;
-                }
-              }
-            }
-#pragma unroll
-            for (int q = 0; q < 8; ++q)
-              *reinterpret_cast<float4*>(wr + ((q ^ (lane & 7)) << 4)) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-            __syncwarp();
-            const int col = nc + rd_chunk * 4;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int row = i * 4 + rd_row;
-              const int mr = mw + row;
-              if (mr < p.M && col < p.N) {
-                float4 y = *reinterpret_cast<const float4*>(stg + row * 128 + ((rd_chunk ^ (row & 7)) << 4));
-                if (p.mode == F5_EPI_RESID_F32) {
-                  float4* x = reinterpret_cast<float4*>(p.resid + static_cast<size_t>(mr) * p.ldr + col);
-                  const float4 x4 = *x;
-                  *x = make_float4(x4.x + y.x, x4.y + y.y, x4.z + y.z, x4.w + y.w);
-                } else {
-                  if (p.addend != nullptr) {
-                    const float4 a4 = *reinterpret_cast<const float4*>(p.addend + static_cast<size_t>(mr) * p.ld_add + col);
-                    y.x += a4.x; y.y += a4.y; y.z += a4.z; y.w += a4.w;
-                  }
-                  *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + static_cast<size_t>(mr) * p.ldo + col) = y;
-                  if (p.out2 != nullptr) {
-                    const bool zr = p.mask_rows && p.row_pos[mr] < 0;
-                    const uint2 w = zr ? make_uint2(0, 0) : make_uint2(pack_bf16x2(y.x, y.y), pack_bf16x2(y.z, y.w));
-                    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out2) + static_cast<size_t>(mr) * p.ldo2 + col) = w;
-                  }
-                }
-              }
-            }
-            __syncwarp();
           }
         }
+        __syncwarp();
       }
       tc_fence_before();
       mbar_arrive(&tmem_empty[acc]);
@@ -341,7 +360,7 @@ int make_tmap_bf16_2d(CUtensorMap* map, const void* base, long long rows, long l
   return r == CUDA_SUCCESS ? F5_OK : F5_ERR_DRIVER;
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, int ACT>
 int launch_gemm(const f5_gemm_args& a, const GemmParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg<BLOCK_N>;
   CUtensorMap ta, tb;
@@ -351,7 +370,7 @@ int launch_gemm(const f5_gemm_args& a, const GemmParams& p, cudaStream_t stream)
   if (rc != F5_OK) return rc;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BLOCK_N, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return static_cast<int>(e);
     attr_set = true;
@@ -359,7 +378,7 @@ int launch_gemm(const f5_gemm_args& a, const GemmParams& p, cudaStream_t stream)
   const int sms = a.num_sms > 0 ? a.num_sms : kNumSMsB200;
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   const int grid = tiles < sms ? tiles : sms;
-  gemm_tcgen05_kernel<BLOCK_N><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, p);
+  gemm_tcgen05_kernel<BLOCK_N, ACT><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, p);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -403,7 +422,16 @@ extern "C" int f5_gemm_bf16(const f5_gemm_args* a, void* stream) {
   }
   if (a->mask_rows && a->row_pos == nullptr) return F5_ERR_ARG;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  if (a->block_n == 256) return launch_gemm<256>(*a, p, s);
-  if (a->block_n == 128) return launch_gemm<128>(*a, p, s);
-  return launch_gemm<64>(*a, p, s);
+  if (a->act < 0 || a->act > 3) return F5_ERR_ARG;
+#define F5_DISPATCH(BN)                                                        \
+  switch (a->act) {                                                            \
+    case F5_ACT_GELU_TANH: return launch_gemm<BN, F5_ACT_GELU_TANH>(*a, p, s); \
+    case F5_ACT_GELU_ERF: return launch_gemm<BN, F5_ACT_GELU_ERF>(*a, p, s);   \
+    case F5_ACT_MISH: return launch_gemm<BN, F5_ACT_MISH>(*a, p, s);           \
+    default: return launch_gemm<BN, F5_ACT_NONE>(*a, p, s);                    \
+  }
+  if (a->block_n == 256) { F5_DISPATCH(256) }
+  if (a->block_n == 128) { F5_DISPATCH(128) }
+  F5_DISPATCH(64)
+#undef F5_DISPATCH
 }
