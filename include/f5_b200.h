@@ -89,8 +89,8 @@ int f5_layernorm_mod(const float* x, int64_t ldx, void* y_bf16, int64_t ldy, flo
 int f5_dwconv7_ln(const float* x, int64_t ldx, void* y, int64_t ldy, int32_t M, int32_t C, const int32_t* row_pos,
                   const float* w, const float* bias, const float* ln_w, const float* ln_b, float eps, void* stream);
 
-/* GRN over each utterance's own rows (model/modules.py:231-234): phase 1 accumulates sum of squares per
- * (segment, channel); phase 2 applies gamma*(x*Nx)+beta+x in place on the bf16 activations. */
+/* GRN over each utterance's own rows (model/modules.py:231-234): phase 1 computes the sum of squares per (segment,
+ * channel) in a fixed order (deterministic, no atomics); phase 2 applies gamma*(x*Nx)+beta+x in place on the bf16 activations. */
 int f5_grn_sumsq(const void* x_bf16, int64_t ldx, int32_t C, const int32_t* seg_rows, int32_t num_segs, float* sumsq,
                  void* stream);
 int f5_grn_apply(void* x_bf16, int64_t ldx, int32_t C, const int32_t* seg_rows, int32_t num_segs, const float* sumsq,

@@ -120,7 +120,7 @@ def test_cfm_sample_api_vs_oracle(tiny_models):
                            cfg_strength=2.0, sway_sampling_coef=-1.0, y0=y0)
     o0, _ = model.sample(cond=mel, text=[texts[0]], duration=80, steps=4, cfg_strength=2.0, sway_sampling_coef=-1.0, y0=y0[:1])
     assert outb.shape == (2, 110, 100) and float(outb[0, 80:].abs().max()) == 0.0
-    assert rel(outb[0, :80].cpu().numpy(), o0[0].cpu().numpy()) < 1e-4      # GRN's atomic sums are the only order-dependent op
+    assert torch.equal(outb[0, :80], o0[0])                                  # deterministic, row-local kernels: bit-exact
     for bad in (dict(duplicate_test=True), dict(cfg_strength=0.0)):
         with pytest.raises(NotImplementedError):
             model.sample(cond=mel, text=[texts[0]], duration=80, **bad)
@@ -167,9 +167,20 @@ def test_packing_invariance_and_graph_equals_eager_full_size(full_models):
     waves = syn.generate(specs, nfe_step=4)
     alone = syn.generate([specs[3]], nfe_step=4)[0]
     s_pack = snr(waves[3], alone)
-    print(f"packed vs alone SNR {s_pack:.1f} dB")
-    assert alone.shape == waves[3].shape and s_pack > 55.0      # bf16 rounding flips seeded by GRN's atomic summation order
+    print(f"packed vs alone (through the batched prompt STFT) SNR {s_pack:.1f} dB")
+    assert alone.shape == waves[3].shape and s_pack > 90.0   # identical up to the batched-vs-single prompt STFT plan
     assert all(np.isfinite(w).all() and np.abs(w).max() > 0 for w in waves)
+    # bit-exact at the sampler level when the inputs are bit-identical (every kernel is deterministic and row-local)
+    mels = [O.mel_spectrogram(sp.audio).permute(0, 2, 1)[0] for sp in specs[:4]]
+    toks = [T.convert_char_to_pinyin([sp.ref_text + sp.gen_text])[0] for sp in specs[:4]]
+    y0 = [S.initial_noise(4096, i) for i in range(4)]
+    durs = torch.tensor([sp.duration for sp in specs[:4]])
+    cond = torch.nn.utils.rnn.pad_sequence(mels, batch_first=True)
+    lens = torch.tensor([m.shape[0] for m in mels])
+    outb, _ = model.sample(cond=cond, text=toks, duration=durs, lens=lens, steps=3, cfg_strength=2.0, sway_sampling_coef=-1.0, y0=y0)
+    out2, _ = model.sample(cond=mels[2][None], text=[toks[2]], duration=int(durs[2]), steps=3, cfg_strength=2.0,
+                           sway_sampling_coef=-1.0, y0=[y0[2]])
+    assert torch.equal(outb[2, : int(durs[2])], out2[0])
     model.engine.use_graphs = False
     try:
         eager = syn.generate(specs, nfe_step=4)
@@ -189,7 +200,7 @@ def test_infer_process_and_manager_surface(tiny_models, tmp_path):
         w.setnchannels(1); w.setsampwidth(2); w.setframerate(24000)
         w.writeframes((audio[0].numpy() * 32767).astype("<i2").tobytes())
     ref_text = T.finish_ref_text(T.synthetic_indic_text(20, 1))
-    gen = ". ".join(T.synthetic_indic_text(60, 10 + i) for i in range(4)) + "."
+    gen = ". ".join(T.synthetic_indic_text(60, 10 + i) for i in range(12)) + "."
     wave, sr, mel = api.infer_process(p, ref_text, gen, model, voc, nfe_step=4)
     assert sr == 24000 and wave.ndim == 1 and mel.shape[0] == 100 and np.isfinite(wave).all()
     nchunks = len(T.chunk_text(gen, int(len(ref_text.encode()) / 1.0 * 24)))

@@ -109,24 +109,29 @@ __global__ void __launch_bounds__(256) dwconv7_ln_kernel(const float* __restrict
 
 // ------------------------------------------------------------------------------------------------ GRN
 constexpr int GRN_ROWS = 32;  // rows per block
-// grid (row chunks of the longest segment, num_segs); block = C/2 threads (bf16x2 per thread)
-__global__ void grn_sumsq_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, int C,
-                                 const int* __restrict__ seg_rows, float* __restrict__ sumsq) {
+// Deterministic (fixed summation order, no atomics): grid (C/128, num_segs); 256 threads = 64 channel pairs x 4 row
+// slices; each thread walks its slice of the utterance's rows in order, the 4 slices are combined in a fixed order.
+__global__ void __launch_bounds__(256) grn_sumsq_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, int C,
+                                                        const int* __restrict__ seg_rows, float* __restrict__ sumsq) {
+  __shared__ float2 part[4][64];
   const int seg = blockIdx.y;
   const int row0 = seg_rows[2 * seg], n = seg_rows[2 * seg + 1];
-  const int r0 = blockIdx.x * GRN_ROWS;
-  if (r0 >= n) return;
-  const int r1 = min(n, r0 + GRN_ROWS);
-  for (int c2 = threadIdx.x; c2 < C / 2; c2 += blockDim.x) {
-    float s0 = 0.f, s1 = 0.f;
-    for (int r = r0; r < r1; ++r) {
-      const __nv_bfloat162 v = reinterpret_cast<const __nv_bfloat162*>(x + static_cast<size_t>(row0 + r) * ldx)[c2];
-      const float2 f = __bfloat1622float2(v);
-      s0 += f.x * f.x;
-      s1 += f.y * f.y;
+  const int cp = threadIdx.x & 63, slice = threadIdx.x >> 6;
+  const int c2 = blockIdx.x * 64 + cp;                 // bf16x2 index
+  float s0 = 0.f, s1 = 0.f;
+  if (2 * c2 < C) {
+    for (int r = slice; r < n; r += 4) {
+      const float2 f = __bfloat1622float2(reinterpret_cast<const __nv_bfloat162*>(x + static_cast<size_t>(row0 + r) * ldx)[c2]);
+      s0 = fmaf(f.x, f.x, s0);
+      s1 = fmaf(f.y, f.y, s1);
     }
-    atomicAdd(&sumsq[static_cast<size_t>(seg) * C + 2 * c2], s0);
-    atomicAdd(&sumsq[static_cast<size_t>(seg) * C + 2 * c2 + 1], s1);
+  }
+  part[slice][cp] = make_float2(s0, s1);
+  __syncthreads();
+  if (slice == 0 && 2 * c2 < C) {
+    const float2 a = part[0][cp], b = part[1][cp], c = part[2][cp], d = part[3][cp];
+    sumsq[static_cast<size_t>(seg) * C + 2 * c2] = (a.x + b.x) + (c.x + d.x);
+    sumsq[static_cast<size_t>(seg) * C + 2 * c2 + 1] = (a.y + b.y) + (c.y + d.y);
   }
 }
 
@@ -304,9 +309,7 @@ static int max_seg_rows_hint = 4096;  // segments never exceed the reference's 4
 extern "C" int f5_grn_sumsq(const void* x, int64_t ldx, int32_t C, const int32_t* seg_rows, int32_t num_segs, float* sumsq,
                             void* stream) {
   if (!x || !seg_rows || !sumsq || num_segs <= 0 || C % 2 != 0 || ldx % 2 != 0) return F5_ERR_ARG;
-  cudaError_t e = cudaMemsetAsync(sumsq, 0, sizeof(float) * static_cast<size_t>(num_segs) * C, F5_STREAM(stream));
-  if (e != cudaSuccess) return static_cast<int>(e);
-  dim3 grid((max_seg_rows_hint + GRN_ROWS - 1) / GRN_ROWS, num_segs);
+  dim3 grid((C + 127) / 128, num_segs);
   grn_sumsq_kernel<<<grid, 256, 0, F5_STREAM(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(x), ldx, C, seg_rows, sumsq);
   return F5_LAUNCH_RC();
 }
