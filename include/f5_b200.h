@@ -73,7 +73,8 @@ int f5_gemm_bf16(const f5_gemm_args* args, void* stream);
  * fp32).  Replaces F.scaled_dot_product_attention at model/modules.py:436 (+ head split/merge :424-437) with
  * per-utterance (batch-1) semantics: a query tile attends to the keys of its own utterance only.
  * qkv: bf16 [rows, ld] with q at column q_col + h*64, k at k_col + h*64, v at v_col + h*64.
- * tiles: int32 [num_tiles, 4] = {q_row0, kv_row0, kv_len, q_rows_valid}.  out: bf16 [rows, ldo], head h at h*64. */
+ * tiles: int32 [num_tiles, 4] = {q_row0, kv_row0, kv_len, q_rows_valid <= 256} — one work item is a PAIR of 128-row query
+ * tiles (x every head); the kernel is persistent (one CTA per SM).  out: bf16 [rows, ldo], head h at h*64. */
 int f5_attention_d64(const void* qkv, int64_t ld, int32_t rows, int32_t q_col, int32_t k_col, int32_t v_col,
                      int32_t heads, const int32_t* tiles, int32_t num_tiles, void* out, int64_t ldo,
                      float softmax_scale, void* stream);

@@ -60,7 +60,7 @@ def test_layout_invariants():
     for q0, kv0, kvl, qv in L.attn_tiles.tolist():
         cover[q0:q0 + qv] += 1
         assert (L.row_pos[kv0:kv0 + kvl] == torch.arange(kvl, dtype=torch.int32)).all()
-        assert kv0 <= q0 < kv0 + kvl
+        assert kv0 <= q0 < kv0 + kvl and 1 <= qv <= 256
     assert torch.equal(cover, (L.row_pos >= 0).to(torch.int32))
     assert L.seg_rows.tolist() == [[h + s, n] for h in (0, R) for s, n in zip(L.starts, lens)]
 

@@ -165,8 +165,8 @@ def _attn_case(lens, H, scale_q=1.0, seed=30):
     qkv[:, :D] *= scale_q
     tiles = []
     for s0, n in zip(starts, lens):
-        for q0 in range(0, n, 128):
-            tiles.append([s0 + q0, s0, n, min(128, n - q0)])
+        for q0 in range(0, n, 256):
+            tiles.append([s0 + q0, s0, n, min(256, n - q0)])
     tiles = torch.tensor(tiles, dtype=torch.int32, device=DEV)
     out = torch.zeros(rows, D, device=DEV, dtype=torch.bfloat16)
     ops.attention(qkv, tiles, out, H, 0, D, 2 * D, 0.125)

@@ -1,0 +1,32 @@
+import ctypes, os, sys
+os.environ["F5_ATTN_TRACE"] = "1"
+import numpy as np, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from tts_indic_server_f5_b200 import ops, _lib
+from tts_indic_server_f5_b200.layout import build_layout
+dev = "cuda"; torch.manual_seed(0)
+g = torch.Generator().manual_seed(0)
+lens = [469 + int(torch.randint(560, 941, (1,), generator=g)) for _ in range(64)]
+L = build_layout(lens); D = 1024
+qkv = torch.randn(L.rows, 3 * D, device=dev).to(torch.bfloat16)
+ab = torch.zeros(L.rows, D, device=dev, dtype=torch.bfloat16)
+tiles = L.attn_tiles.to(dev)
+for _ in range(3):
+    ops.attention(qkv, tiles, ab, 16, 0, D, 2 * D, 0.125)
+torch.cuda.synchronize()
+buf = (ctypes.c_longlong * 2048)()
+_lib.lib.f5_attention_trace_dump.argtypes = [ctypes.c_void_p]
+print("rc", _lib.lib.f5_attention_trace_dump(buf))
+a = np.array(buf[:], dtype=np.int64).reshape(4, 512)
+t0 = a[a > 0].min()
+prod = a[0][a[0] > 0] - t0
+print("producer kv-load issue times (first 24):", prod[:24].tolist())
+m = a[1][a[1] > 0] - t0
+print("MMA events (per iter: top, pA, issuedA, pB, issuedB) first 40:", m[:40].tolist())
+for r in (2, 3):
+    s = a[r][:160].reshape(-1, 4)
+    s = s[(s > 0).all(axis=1)] - t0
+    print(f"softmax group {r-2}: per tile [s_full seen, S loaded+max, o_full ok, arrived] first 12:")
+    for row in s[:12]: print("   ", row.tolist(), " softmax dur", int(row[3] - row[0]))
+    d = np.diff(s[:, 0])
+    print("   tile period (s_full to s_full):", d[:16].tolist())

@@ -52,3 +52,24 @@ run("N=1024 store bf16 K2048", 1024, 2048, 0, 0)
 run("N=1024 store f32", 1024, 1024, 1, 0)
 run("qkv bn128", 3072, 1024, 0, 0, bn=128)
 run("ff1 bn128 gelu", 2048, 1024, 0, 1, bn=128)
+
+# attention at C2 scale
+from tts_indic_server_f5_b200.layout import build_layout  # noqa: E402
+g = torch.Generator().manual_seed(0)
+lens = [469 + int(torch.randint(560, 941, (1,), generator=g)) for _ in range(64)]
+L = build_layout(lens)
+D = 1024
+qkv = torch.randn(L.rows, 3 * D, device=dev).to(torch.bfloat16)
+ab = torch.zeros(L.rows, D, device=dev, dtype=torch.bfloat16)
+tiles = L.attn_tiles.to(dev)
+for _ in range(2):
+    ops.attention(qkv, tiles, ab, 16, 0, D, 2 * D, 0.125)
+e = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
+e[0].record()
+for i in range(5):
+    ops.attention(qkv, tiles, ab, 16, 0, D, 2 * D, 0.125)
+    e[i + 1].record()
+torch.cuda.synchronize()
+t = sorted(e[i].elapsed_time(e[i + 1]) for i in range(5))[2]
+fl = 2 * sum(4.0 * D * n * n for n in lens)
+print(f"attention C2 (64 utts x2, 16 heads): {t * 1e3:8.1f} us  {fl / t / 1e9:7.1f} TFLOP/s", flush=True)

@@ -1,33 +1,43 @@
 // Non-causal variable-length flash attention, head_dim 64, on tcgen05 (sm_100a).
 //
-// One CTA = one (query tile of 128 rows, head).  Keys/values of the query's own utterance are streamed in tiles of
-// 128 through a 2-stage TMA ring.
-//   warp 0    : TMA producer (Q once, then K_j / V_j)
-//   warp 1    : MMA issuer: S = Q K_j^T  (128x128x64, SS) -> TMEM cols [0,128);   O += P_j V_j (128x64x128) -> TMEM cols [128,192)
-//   warps 2-5 : online softmax, one thread per query row (= TMEM lane): two passes over S in TMEM (row max; exp2 + row sum),
-//               P_j written as bf16 into a 128B-swizzled K-major smem tile, O rescaled in TMEM when the running max moved.
-// Two CTAs fit per SM (112 KB smem, 256 TMEM columns each) so one CTA's softmax overlaps the other's MMAs.
-//
-// V tiles [keys, d] are read straight from the qkv buffer and fed to the PV MMA as an MN-major B operand (no transpose pass).
+// Persistent: one CTA per SM walks a list of work items = (pair of 128-row query tiles of one utterance, head).
+//   warp 0     : TMA producer  (Q pair once per item; K_j / V_j tiles of 128 keys through a 2-stage ring)
+//   warp 1     : MMA issuer    S_g = Q_g K_j^T (128x128x64, SS) -> TMEM;  O_g += P_g V_j (128x64x128, V as MN-major B operand
+//                              read straight from the QKV buffer — no transpose pass) -> TMEM           (g = tile A / tile B)
+//   warps 2-5  : softmax group A, warps 6-9: softmax group B — one thread per query row (= TMEM lane): row max, exp2 with
+//                packed FFMA2/FADD2, P_g as bf16 into a 128B-swizzled smem tile, lazy rescale of O_g in TMEM, final O/l store.
+// The two groups ping-pong on the SAME K/V tiles: while group A runs its exps (MUFU-bound: 16 k exps per tile vs 512 MMA
+// cycles) the tensor core works for group B and vice versa, so neither the MUFU nor the tensor pipe waits on the
+// softmax -> MMA -> softmax dependency chain of a single tile.  TMEM: S_A | S_B | O_A | O_B = 384 of 512 columns.
 #include "f5_common.cuh"
 #include "../../include/f5_b200.h"
+#include <cstdlib>
 
 namespace f5 {
 
-constexpr int ATT_THREADS = 192;
-constexpr int ATT_BM = 128;   // query rows per CTA
+constexpr int ATT_THREADS = 320;
+constexpr int ATT_BM = 128;   // query rows per tile (two tiles per work item)
 constexpr int ATT_BN = 128;   // keys per tile
 constexpr int ATT_D = 64;
 constexpr int ATT_TILE_BYTES = 128 * 64 * 2;  // 16 KB
-constexpr int ATT_SMEM = ATT_TILE_BYTES * (1 + 2 + 2 + 2) + 128;   // 112 KB + barriers: two CTAs per SM
-constexpr int ATT_TMEM_COLS = 256;
+constexpr int ATT_KV_STAGES = 2;
+constexpr int ATT_SMEM = ATT_TILE_BYTES * (2 /*Q*/ + 2 * ATT_KV_STAGES /*K,V*/ + 8 /*P_A,P_B double-buffered*/) + 256;
+constexpr int ATT_TMEM_COLS = 512;
+#ifndef ATT_POLY_COUNT
+#define ATT_POLY_COUNT 0      // of every ATT_POLY_PERIOD score pairs, this many take the polynomial exp2 path (measured on B200: 25-50 % offload was NOT faster — the FMA/ALU pipes are already busy with scale, sum, max and bf16 packing)
+#endif
+#ifndef ATT_POLY_PERIOD
+#define ATT_POLY_PERIOD 4
+#endif
 
 struct AttnParams {
-  int q_col, k_col, v_col;
-  const int* tiles;  // [num_tiles][4] = q_row0, kv_row0, kv_len, q_rows_valid
+  int q_col, k_col, v_col, heads;
+  const int* items;   // [num_pairs][4] = q_row0, kv_row0, kv_len, q_rows_valid (1..256)
+  int num_work;       // num_pairs * heads
   __nv_bfloat16* out;
   long long ldo;
   float scale_log2;
+  long long* trace;   // optional clock64 event trace of CTA 0 (F5_ATTN_TRACE), [4 roles][512]
 };
 
 __device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_t (&r)[32]) {
@@ -54,38 +64,41 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr) {
   return d;
 }
 
-__global__ void __launch_bounds__(ATT_THREADS, 2)
+#define F5_TRACE(role, idx) do { if (p.trace != nullptr && blockIdx.x == 0 && (idx) < 512) p.trace[(role) * 512 + (idx)] = clock64(); } while (0)
+
+__global__ void __launch_bounds__(ATT_THREADS, 1)
 attn_d64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();   // 128B-swizzled tiles need 1024-B aligned bases
-  uint8_t* sQ = smem;
-  uint8_t* sK = sQ + ATT_TILE_BYTES;          // 2 stages
-  uint8_t* sV = sK + 2 * ATT_TILE_BYTES;      // 2 stages
-  uint8_t* sP = sV + 2 * ATT_TILE_BYTES;      // 2 K-atom blocks of 16 KB
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * ATT_TILE_BYTES);
-  uint64_t* q_full = bars;
-  uint64_t* kv_full = bars + 1;    // [2]
-  uint64_t* kv_empty = bars + 3;   // [2]
-  uint64_t* s_full = bars + 5;
-  uint64_t* p_full = bars + 6;
-  uint64_t* o_full = bars + 7;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 8);
+  uint8_t* sQ = smem;                                         // [2] tiles A, B
+  uint8_t* sK = sQ + 2 * ATT_TILE_BYTES;                      // [ATT_KV_STAGES]
+  uint8_t* sV = sK + ATT_KV_STAGES * ATT_TILE_BYTES;          // [ATT_KV_STAGES]
+  uint8_t* sP = sV + ATT_KV_STAGES * ATT_TILE_BYTES;          // [2 groups][2 buffers][2 K-atom blocks of 16 KB]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 8 * ATT_TILE_BYTES);
+  uint64_t* q_full = bars;          // 1
+  uint64_t* q_empty = bars + 1;     // 1
+  uint64_t* kv_full = bars + 2;     // [ATT_KV_STAGES <= 3]
+  uint64_t* kv_empty = bars + 5;    // [ATT_KV_STAGES <= 3]
+  uint64_t* s_full = bars + 8;      // [2]
+  uint64_t* p_full = bars + 10;     // [2]
+  uint64_t* o_full = bars + 12;     // [2]
+  uint64_t* o_free = bars + 14;     // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 16);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int head = blockIdx.y;
-  const int4 tile = *reinterpret_cast<const int4*>(p.tiles + 4 * blockIdx.x);
-  const int q_row0 = tile.x, kv_row0 = tile.y, kv_len = tile.z, q_valid = tile.w;
-  const int nkv = (kv_len + ATT_BN - 1) / ATT_BN;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_qkv);
     mbar_init(q_full, 1);
-    mbar_init(&kv_full[0], 1); mbar_init(&kv_full[1], 1);
-    mbar_init(&kv_empty[0], 1); mbar_init(&kv_empty[1], 1);
-    mbar_init(s_full, 1);
-    mbar_init(p_full, 128);
-    mbar_init(o_full, 1);
+    mbar_init(q_empty, 1);
+    for (int i = 0; i < ATT_KV_STAGES; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+    for (int g = 0; g < 2; ++g) {
+      mbar_init(&s_full[g], 1);
+      mbar_init(&p_full[g], 128);
+      mbar_init(&o_full[g], 1);
+      mbar_init(&o_free[g], 128);
+    }
     mbar_fence_init();
   }
   if (warp == 1) {
@@ -96,177 +109,237 @@ attn_d64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnParams p
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
-  const uint32_t tmem_S = tmem_base;
-  const uint32_t tmem_O = tmem_base + ATT_BN;
 
   if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      mbar_expect_tx(q_full, ATT_TILE_BYTES);
-      tma_load_2d(sQ, &tmap_qkv, q_full, p.q_col + head * ATT_D, q_row0);
-      for (int j = 0; j < nkv; ++j) {
-        const int st = j & 1;
-        mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1);
-        mbar_expect_tx(&kv_full[st], 2 * ATT_TILE_BYTES);
-        tma_load_2d(sK + st * ATT_TILE_BYTES, &tmap_qkv, &kv_full[st], p.k_col + head * ATT_D, kv_row0 + j * ATT_BN);
-        tma_load_2d(sV + st * ATT_TILE_BYTES, &tmap_qkv, &kv_full[st], p.v_col + head * ATT_D, kv_row0 + j * ATT_BN);
+      uint32_t item = 0, g_kv = 0;
+      for (int w = blockIdx.x; w < p.num_work; w += gridDim.x, ++item) {
+        const int4 it = *reinterpret_cast<const int4*>(p.items + 4 * (w / p.heads));
+        const int head = w % p.heads;
+        const int nkv = (it.z + ATT_BN - 1) / ATT_BN;
+        mbar_wait(q_empty, (item & 1) ^ 1);                    // previous item's last QK has retired
+        mbar_expect_tx(q_full, (it.w > ATT_BM ? 2 : 1) * ATT_TILE_BYTES);
+        tma_load_2d(sQ, &tmap_qkv, q_full, p.q_col + head * ATT_D, it.x);
+        if (it.w > ATT_BM) tma_load_2d(sQ + ATT_TILE_BYTES, &tmap_qkv, q_full, p.q_col + head * ATT_D, it.x + ATT_BM);
+        for (int j = 0; j < nkv; ++j, ++g_kv) {
+          const uint32_t st = g_kv % ATT_KV_STAGES, ph = (g_kv / ATT_KV_STAGES) & 1;
+          mbar_wait(&kv_empty[st], ph ^ 1);
+          mbar_expect_tx(&kv_full[st], 2 * ATT_TILE_BYTES);
+          tma_load_2d(sK + st * ATT_TILE_BYTES, &tmap_qkv, &kv_full[st], p.k_col + head * ATT_D, it.y + j * ATT_BN);
+          tma_load_2d(sV + st * ATT_TILE_BYTES, &tmap_qkv, &kv_full[st], p.v_col + head * ATT_D, it.y + j * ATT_BN);
+          F5_TRACE(0, g_kv);
+        }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer
+    // The WHOLE warp walks the loop (warp-uniform control flow keeps descriptors / addresses in uniform registers, which is
+    // what UTCHMMA consumes); only the tcgen05.mma / commit instructions themselves are predicated on one elected lane.
+    // Issuing from inside a divergent `if (lane == 0)` region costs a serial R2UR chain per MMA (~85 cycles each, measured),
+    // which made 24 MMAs per tile pair slower than the tensor work they describe.
+    {
       constexpr uint32_t idesc_qk = umma_idesc_bf16(ATT_BM, ATT_BN);
       constexpr uint32_t idesc_pv = umma_idesc_bf16(ATT_BM, ATT_D) | (1u << 16);   // B (= V) is MN-major
-      const uint64_t qdesc = umma_desc_k_sw128(smem_u32(sQ));
-      mbar_wait(q_full, 0);
-      mbar_wait(&kv_full[0], 0);
-      tc_fence_after();
-      {
-        const uint64_t kdesc = umma_desc_k_sw128(smem_u32(sK));
+      const bool leader = elect_one();
+      const uint64_t qd0 = umma_desc_k_sw128(smem_u32(sQ));
+      const uint64_t kd0 = umma_desc_k_sw128(smem_u32(sK));
+      const uint64_t pd0 = umma_desc_k_sw128(smem_u32(sP));
+      const uint64_t vd0 = umma_desc_mn_sw128(smem_u32(sV));
+      constexpr uint64_t TILE16 = ATT_TILE_BYTES >> 4;      // descriptor address field is in 16-B units
+      uint32_t item = 0, g_kv = 0, ev = 0;
+      uint32_t t[2] = {0, 0};        // tiles processed so far per group (phase of s_full / p_full / o_full)
+      uint32_t it_g[2] = {0, 0};     // items processed so far per group (phase of o_free)
+      auto issue_qk = [&](int g, uint32_t st) {
+        const uint64_t qd = qd0 + g * TILE16, kd = kd0 + st * TILE16;
+        if (leader) {
 #pragma unroll
-        for (int kk = 0; kk < ATT_D / 16; ++kk) umma_f16_ss(tmem_S, qdesc + 2 * kk, kdesc + 2 * kk, idesc_qk, kk != 0);
-        umma_commit(s_full);
-      }
-      for (int j = 0; j < nkv; ++j) {
-        const int st = j & 1;
-        mbar_wait(p_full, j & 1);          // softmax consumed S_j, wrote P_j and rescaled O
-        tc_fence_after();
-        if (j + 1 < nkv) {
-          const int sn = (j + 1) & 1;
-          mbar_wait(&kv_full[sn], ((j + 1) >> 1) & 1);
+          for (int kk = 0; kk < ATT_D / 16; ++kk)
+            umma_f16_ss(tmem_base + g * ATT_BN, qd + 2 * kk, kd + 2 * kk, idesc_qk, kk != 0);
+          umma_commit(&s_full[g]);
+        }
+        __syncwarp();
+      };
+      auto issue_pv = [&](int g, uint32_t st, bool first) {
+        const uint64_t pd = pd0 + (g * 4 + (t[g] & 1) * 2) * TILE16, vd = vd0 + st * TILE16;
+        if (leader) {
+#pragma unroll
+          for (int kk = 0; kk < ATT_BN / 16; ++kk)            // 16 keys = 2 KB (128 x 16 B) of the V tile per MMA
+            umma_f16_ss(tmem_base + 2 * ATT_BN + g * ATT_D, pd + (kk >> 2) * TILE16 + 2 * (kk & 3), vd + kk * 128, idesc_pv,
+                        (!first || kk != 0) ? 1u : 0u);
+          umma_commit(&o_full[g]);
+        }
+        __syncwarp();
+      };
+      for (int w = blockIdx.x; w < p.num_work; w += gridDim.x, ++item) {
+        const int4 it = *reinterpret_cast<const int4*>(p.items + 4 * (w / p.heads));
+        const int nkv = (it.z + ATT_BN - 1) / ATT_BN;
+        const int ngroups = it.w > ATT_BM ? 2 : 1;
+        mbar_wait(q_full, item & 1);
+        {
+          const uint32_t st = g_kv % ATT_KV_STAGES, ph = (g_kv / ATT_KV_STAGES) & 1;
+          mbar_wait(&kv_full[st], ph);
           tc_fence_after();
-          const uint64_t kdesc = umma_desc_k_sw128(smem_u32(sK + sn * ATT_TILE_BYTES));
-#pragma unroll
-          for (int kk = 0; kk < ATT_D / 16; ++kk) umma_f16_ss(tmem_S, qdesc + 2 * kk, kdesc + 2 * kk, idesc_qk, kk != 0);
-          umma_commit(s_full);
+          for (int g = 0; g < ngroups; ++g) issue_qk(g, st);
+          if (nkv == 1 && leader) umma_commit(q_empty);      // every QK of this item is issued: the Q tiles may be refilled
         }
-        const uint32_t sp = smem_u32(sP);
-        const uint32_t sv = smem_u32(sV + st * ATT_TILE_BYTES);
-#pragma unroll
-        for (int kk = 0; kk < ATT_BN / 16; ++kk) {
-          const uint64_t pdesc = umma_desc_k_sw128(sp + (kk >> 2) * ATT_TILE_BYTES) + 2 * (kk & 3);
-          umma_f16_ss(tmem_O, pdesc, umma_desc_mn_sw128(sv + kk * 2048), idesc_pv, (j | kk) != 0);   // 16 keys = 2 KB
+        for (int j = 0; j < nkv; ++j, ++g_kv) {
+          const uint32_t st = g_kv % ATT_KV_STAGES;
+          const bool more = j + 1 < nkv;
+          uint32_t stn = 0;
+          if (more) {
+            stn = (g_kv + 1) % ATT_KV_STAGES;
+            mbar_wait(&kv_full[stn], ((g_kv + 1) / ATT_KV_STAGES) & 1);
+          }
+          if (lane == 0) { F5_TRACE(1, ev); }
+          ++ev;
+          for (int g = 0; g < ngroups; ++g) {
+            mbar_wait(&p_full[g], t[g] & 1);       // group g consumed S_g(j) and wrote P_g(j)
+            tc_fence_after();
+            if (lane == 0) { F5_TRACE(1, ev); }
+            ++ev;
+            if (more) issue_qk(g, stn);            // S_g is free again: next scores first, so group g never waits on its own PV
+            if (j == 0) {                          // O_g of the previous item must have been read out
+              mbar_wait(&o_free[g], (it_g[g] & 1) ^ 1);
+              tc_fence_after();
+            }
+            issue_pv(g, st, j == 0);
+            if (lane == 0) { F5_TRACE(1, ev); }
+            ++ev;
+            ++t[g];
+          }
+          if (leader) {
+            umma_commit(&kv_empty[st]);              // both groups' PV on (K_j, V_j) retired -> stage reusable
+            if (more && j + 2 == nkv) umma_commit(q_empty);   // the last tile's QKs were just issued: next item's Q may load
+          }
+          __syncwarp();
         }
-        umma_commit(&kv_empty[st]);
-        umma_commit(o_full);
+        for (int g = 0; g < ngroups; ++g) ++it_g[g];
       }
     }
   } else {
-    const int quarter = warp & 3;
+    // ------------------------------------------------------------------ softmax groups
+    const int g = (warp - 2) >> 2;                // 0: tile A, 1: tile B
+    const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
     const int row = quarter * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
-    float m_run = -INFINITY, l_run = 0.f;
+    const uint32_t tmem_S = tmem_base + g * ATT_BN;
+    const uint32_t tmem_O = tmem_base + 2 * ATT_BN + g * ATT_D;
+    uint8_t* sPg = sP + g * 4 * ATT_TILE_BYTES;
     const float2 sc2 = make_float2(p.scale_log2, p.scale_log2);
-    for (int j = 0; j < nkv; ++j) {
-      const int kv_valid = min(ATT_BN, kv_len - j * ATT_BN);
-      const bool full = kv_valid == ATT_BN;           // only the last tile of an utterance needs key masking
-      mbar_wait(s_full, j & 1);
-      tc_fence_after();
-      // pass 1: row max of the raw scores (S stays in TMEM; re-reading it is cheaper than holding 128 registers)
-      float mx = -INFINITY;
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        uint32_t r0[32], r1[32];
-        tmem_ld_32x32b_x32(tmem_S + lane_off + h * 64, r0);
-        tmem_ld_32x32b_x32(tmem_S + lane_off + h * 64 + 32, r1);
-        tmem_ld_wait();
-        if (full) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaxf(__uint_as_float(r0[i]), __uint_as_float(r1[i])));
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            if (h * 64 + i < kv_valid) mx = fmaxf(mx, __uint_as_float(r0[i]));
-            if (h * 64 + 32 + i < kv_valid) mx = fmaxf(mx, __uint_as_float(r1[i]));
-          }
-        }
-      }
-      // lazy rescale: keep a stale running max while it is within 2^8 of the true one (p <= 256 is harmless in bf16/fp32);
-      // O and l are only rescaled when the max really moved.  The first tile always "grows" (m_run = -inf, alpha = 0).
-      const float m_new = fmaxf(m_run, mx * p.scale_log2);
-      const bool grow = (m_new - m_run) > 8.f;
-      const bool any_grow = __any_sync(0xffffffffu, grow);
-      float alpha = 1.f;
-      if (grow) {
-        alpha = fast_ex2(m_run - m_new);
-        m_run = m_new;
-      }
-      // previous PV must be complete before P is overwritten / O is rescaled
-      if (j > 0) {
-        mbar_wait(o_full, (j - 1) & 1);
+    uint32_t t = 0;
+    for (int w = blockIdx.x; w < p.num_work; w += gridDim.x) {
+      const int4 it = *reinterpret_cast<const int4*>(p.items + 4 * (w / p.heads));
+      const int head = w % p.heads;
+      const int q_valid = it.w - g * ATT_BM;      // rows of this group's tile that exist
+      if (q_valid <= 0) continue;                 // tile B absent: the MMA warp skips this group too
+      const int kv_len = it.z;
+      const int nkv = (kv_len + ATT_BN - 1) / ATT_BN;
+      float m_run = -INFINITY, l_run = 0.f;
+      for (int j = 0; j < nkv; ++j, ++t) {
+        const int kv_valid = min(ATT_BN, kv_len - j * ATT_BN);
+        const bool full = kv_valid == ATT_BN;     // only the last tile of an utterance needs key masking
+        mbar_wait(&s_full[g], t & 1);
         tc_fence_after();
-      }
-      // pass 2: p = exp2(s*scale - m), row sum, bf16 P -> swizzled smem
-      const float2 nm2 = make_float2(-m_run, -m_run);
-      float2 ls2 = make_float2(0.f, 0.f);
-#pragma unroll
-      for (int c = 0; c < ATT_BN / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(tmem_S + lane_off + c * 32, r);
+        if (row == 0) F5_TRACE(2 + g, 4 * t);
+        // S row (128 fp32) is read from TMEM ONCE into registers: LDTM bandwidth, not MUFU, limited the two-pass version.
+        uint32_t r[128];
+        tmem_ld_32x32b_x32(tmem_S + lane_off, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
+        tmem_ld_32x32b_x32(tmem_S + lane_off + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
+        tmem_ld_32x32b_x32(tmem_S + lane_off + 64, *reinterpret_cast<uint32_t(*)[32]>(&r[64]));
+        tmem_ld_32x32b_x32(tmem_S + lane_off + 96, *reinterpret_cast<uint32_t(*)[32]>(&r[96]));
         tmem_ld_wait();
-        uint32_t pk[16];
-        if (full) {
+        if (!full) {
+#pragma unroll
+          for (int i = 0; i < 128; ++i)
+            if (i >= kv_valid) r[i] = 0xff800000u;   // -inf: masked keys drop out of the max and give exp2 = 0
+        }
+        float mx = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 64; ++i) mx = fmaxf(mx, fmaxf(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])));
+        if (row == 0) F5_TRACE(2 + g, 4 * t + 1);
+        // lazy rescale: keep a stale running max while it is within 2^8 of the true one (p <= 256 is harmless in bf16/fp32);
+        // O and l are only rescaled when the max really moved.  The first tile always "grows" (m_run = -inf, alpha = 0).
+        const float m_new = fmaxf(m_run, mx * p.scale_log2);
+        const bool grow = (m_new - m_run) > 8.f;
+        const bool any_grow = __any_sync(0xffffffffu, grow);
+        float alpha = 1.f;
+        if (grow) {
+          alpha = fast_ex2(m_run - m_new);
+          m_run = m_new;
+        }
+        // p = exp2(s*scale - m), row sum, bf16 P -> swizzled smem.  P_g is double-buffered: the buffer written for tile t was
+        // last read by PV_g(t-2), which retired before QK_g(t) (in-order tensor pipe) — no wait on the previous PV needed.
+        if (row == 0) F5_TRACE(2 + g, 4 * t + 2);
+        const float2 nm2 = make_float2(-m_run, -m_run);
+        float2 ls2 = make_float2(0.f, 0.f);
+        uint8_t* sPt = sPg + (t & 1) * 2 * ATT_TILE_BYTES;
+#pragma unroll
+        for (int c = 0; c < ATT_BN / 32; ++c) {
+          uint32_t pk[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            float2 t = ffma2(make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), sc2, nm2);
-            t.x = fast_ex2(t.x);
-            t.y = fast_ex2(t.y);
-            ls2 = fadd2(ls2, t);
-            pk[i] = pack_bf16x2(t.x, t.y);
+            float2 e = ffma2(make_float2(__uint_as_float(r[c * 32 + 2 * i]), __uint_as_float(r[c * 32 + 2 * i + 1])), sc2, nm2);
+            if ((i % ATT_POLY_PERIOD) < ATT_POLY_COUNT) {   // this pair on the FMA/ALU pipes, the others on the MUFU
+              e = exp2_poly2(e);
+            } else {
+              e.x = fast_ex2(e.x);
+              e.y = fast_ex2(e.y);
+            }
+            ls2 = fadd2(ls2, e);
+            pk[i] = pack_bf16x2(e.x, e.y);
           }
-        } else {
+          uint8_t* blk = sPt + (c >> 1) * ATT_TILE_BYTES + row * 128;
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int k0 = c * 32 + 2 * i;
-            const float e0 = k0 < kv_valid ? fast_ex2(fmaf(__uint_as_float(r[2 * i]), p.scale_log2, -m_run)) : 0.f;
-            const float e1 = k0 + 1 < kv_valid ? fast_ex2(fmaf(__uint_as_float(r[2 * i + 1]), p.scale_log2, -m_run)) : 0.f;
-            ls2.x += e0;
-            ls2.y += e1;
-            pk[i] = pack_bf16x2(e0, e1);
+          for (int q = 0; q < 4; ++q) {
+            const int chunk = (c & 1) * 4 + q;
+            *reinterpret_cast<uint4*>(blk + ((chunk ^ (row & 7)) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
           }
         }
-        uint8_t* blk = sP + (c >> 1) * ATT_TILE_BYTES + row * 128;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int chunk = (c & 1) * 4 + q;
-          *reinterpret_cast<uint4*>(blk + ((chunk ^ (row & 7)) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
-        }
-      }
-      l_run = l_run * alpha + (ls2.x + ls2.y);
-      if (j > 0 && any_grow) {
+        l_run = l_run * alpha + (ls2.x + ls2.y);
+        if (j > 0 && any_grow) {
+          mbar_wait(&o_full[g], (t - 1) & 1);     // the previous PV of this group must have retired before O is rescaled
+          tc_fence_after();
 #pragma unroll 1
-        for (int c = 0; c < ATT_D / 32; ++c) {
-          uint32_t r[32];
-          tmem_ld_32x32b_x32(tmem_O + lane_off + c * 32, r);
-          tmem_ld_wait();
+          for (int c = 0; c < ATT_D / 32; ++c) {
+            uint32_t ro[32];
+            tmem_ld_32x32b_x32(tmem_O + lane_off + c * 32, ro);
+            tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
-          tmem_st_32x32b_x32(tmem_O + lane_off + c * 32, r);
+            for (int i = 0; i < 32; ++i) ro[i] = __float_as_uint(__uint_as_float(ro[i]) * alpha);
+            tmem_st_32x32b_x32(tmem_O + lane_off + c * 32, ro);
+          }
+          tmem_st_wait();
         }
-        tmem_st_wait();
+        fence_proxy_async_smem();
+        tc_fence_before();
+        mbar_arrive(&p_full[g]);
+        if (row == 0) F5_TRACE(2 + g, 4 * t + 3);
       }
-      fence_proxy_async_smem();
+      // epilogue of the item: O / l -> bf16 rows of the output
+      mbar_wait(&o_full[g], (t - 1) & 1);
+      tc_fence_after();
+      const float inv_l = 1.f / l_run;
+#pragma unroll 1
+      for (int c = 0; c < ATT_D / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(tmem_O + lane_off + c * 32, r);
+        tmem_ld_wait();
+        if (row < q_valid) {
+          __nv_bfloat16* o = p.out + static_cast<size_t>(it.x + g * ATT_BM + row) * p.ldo + head * ATT_D + c * 32;
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) {
+            uint4 wv;
+            wv.x = pack_bf16x2(__uint_as_float(r[i]) * inv_l, __uint_as_float(r[i + 1]) * inv_l);
+            wv.y = pack_bf16x2(__uint_as_float(r[i + 2]) * inv_l, __uint_as_float(r[i + 3]) * inv_l);
+            wv.z = pack_bf16x2(__uint_as_float(r[i + 4]) * inv_l, __uint_as_float(r[i + 5]) * inv_l);
+            wv.w = pack_bf16x2(__uint_as_float(r[i + 6]) * inv_l, __uint_as_float(r[i + 7]) * inv_l);
+            *reinterpret_cast<uint4*>(o + i) = wv;
+          }
+        }
+      }
       tc_fence_before();
-      mbar_arrive(p_full);
-    }
-    mbar_wait(o_full, (nkv - 1) & 1);
-    tc_fence_after();
-    const float inv_l = 1.f / l_run;
-#pragma unroll 1
-    for (int c = 0; c < ATT_D / 32; ++c) {
-      uint32_t r[32];
-      tmem_ld_32x32b_x32(tmem_O + lane_off + c * 32, r);
-      tmem_ld_wait();
-      if (row < q_valid) {
-        __nv_bfloat16* o = p.out + static_cast<size_t>(q_row0 + row) * p.ldo + head * ATT_D + c * 32;
-#pragma unroll
-        for (int i = 0; i < 32; i += 8) {
-          uint4 w;
-          w.x = pack_bf16x2(__uint_as_float(r[i]) * inv_l, __uint_as_float(r[i + 1]) * inv_l);
-          w.y = pack_bf16x2(__uint_as_float(r[i + 2]) * inv_l, __uint_as_float(r[i + 3]) * inv_l);
-          w.z = pack_bf16x2(__uint_as_float(r[i + 4]) * inv_l, __uint_as_float(r[i + 5]) * inv_l);
-          w.w = pack_bf16x2(__uint_as_float(r[i + 6]) * inv_l, __uint_as_float(r[i + 7]) * inv_l);
-          *reinterpret_cast<uint4*>(o + i) = w;
-        }
-      }
+      mbar_arrive(&o_free[g]);                    // O_g may be overwritten by the next item's first PV
     }
   }
 
@@ -279,14 +352,21 @@ attn_d64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnParams p
 }
 
 int make_tmap_bf16_2d(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, int box_rows);
+static long long* g_trace_buf = nullptr;
 
 }  // namespace f5
 
+extern "C" int f5_attention_trace_dump(long long* host) {
+  if (f5::g_trace_buf == nullptr) return F5_ERR_ARG;
+  cudaDeviceSynchronize();
+  return static_cast<int>(cudaMemcpy(host, f5::g_trace_buf, 4 * 512 * sizeof(long long), cudaMemcpyDeviceToHost));
+}
+
 extern "C" int f5_attention_d64(const void* qkv, int64_t ld, int32_t rows, int32_t q_col, int32_t k_col, int32_t v_col,
-                                int32_t heads, const int32_t* tiles, int32_t num_tiles, void* out, int64_t ldo,
+                                int32_t heads, const int32_t* items, int32_t num_items, void* out, int64_t ldo,
                                 float softmax_scale, void* stream) {
   using namespace f5;
-  if (qkv == nullptr || tiles == nullptr || out == nullptr || num_tiles <= 0 || heads <= 0) return F5_ERR_ARG;
+  if (qkv == nullptr || items == nullptr || out == nullptr || num_items <= 0 || heads <= 0) return F5_ERR_ARG;
   if ((ldo % 8) != 0) return F5_ERR_ARG;
   const int cols = (q_col > k_col ? (q_col > v_col ? q_col : v_col) : (k_col > v_col ? k_col : v_col)) + heads * ATT_D;
   CUtensorMap tq;
@@ -299,12 +379,20 @@ extern "C" int f5_attention_d64(const void* qkv, int64_t ld, int32_t rows, int32
     attr_set = true;
   }
   AttnParams p;
-  p.q_col = q_col; p.k_col = k_col; p.v_col = v_col;
-  p.tiles = tiles;
+  p.q_col = q_col; p.k_col = k_col; p.v_col = v_col; p.heads = heads;
+  p.items = items;
+  p.num_work = num_items * heads;
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
   p.ldo = ldo;
   p.scale_log2 = softmax_scale * 1.4426950408889634f;
-  dim3 grid(num_tiles, heads);
+  static long long* trace_buf = nullptr;
+  if (getenv("F5_ATTN_TRACE") != nullptr && trace_buf == nullptr) {
+    cudaMalloc(&trace_buf, 4 * 512 * sizeof(long long));
+    cudaMemset(trace_buf, 0, 4 * 512 * sizeof(long long));
+  }
+  p.trace = trace_buf;
+  g_trace_buf = trace_buf;
+  const int grid = p.num_work < kNumSMsB200 ? p.num_work : kNumSMsB200;
   attn_d64_kernel<<<grid, ATT_THREADS, ATT_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(tq, p);
   return static_cast<int>(cudaGetLastError());
 }

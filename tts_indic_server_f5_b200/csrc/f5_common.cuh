@@ -54,14 +54,20 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// try_wait suspends the thread in hardware for a bounded time, so the loop is not a hot spin; the watchdog clock is only
+// read every 4096 polls to keep the polling warps (one lane each) off the issue slots the math warps need.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > F5_WATCHDOG_CYCLES) {
-      printf("f5: mbarrier watchdog: block %d thread %d bar %u parity %u\n", blockIdx.x, threadIdx.x,
-             smem_u32(bar), parity);
-      __trap();
+  long long t0 = 0;
+  for (uint32_t polls = 1;; ++polls) {
+    if (mbar_try_wait(bar, parity)) return;
+    if ((polls & 4095u) == 0) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      if (now - t0 > F5_WATCHDOG_CYCLES) {
+        printf("f5: mbarrier watchdog: block %d thread %d bar %u parity %u\n", blockIdx.x, threadIdx.x, smem_u32(bar), parity);
+        __trap();
+      }
     }
   }
 }
@@ -217,6 +223,27 @@ __device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
       : "=l"(reinterpret_cast<uint64_t&>(d))
       : "l"(reinterpret_cast<const uint64_t&>(a)), "l"(reinterpret_cast<const uint64_t&>(b)));
   return d;
+}
+// exp2 on the FMA/ALU pipes for a pair of values (Cody-Waite split + degree-3 minimax polynomial, rel. error ~1e-4 — far
+// below the bf16 rounding of P).  Used for a fraction of the softmax exponentials so that the MUFU (16 ex2/clk/SM) is not
+// the only unit doing them.  Inputs must be <= ~100; they are clamped at -126 (2^-126 stands in for exp2(-inf) = 0).
+__device__ __forceinline__ float2 exp2_poly2(float2 x) {
+  x.x = fmaxf(x.x, -126.f);
+  x.y = fmaxf(x.y, -126.f);
+  const float2 magic = make_float2(12582912.f, 12582912.f);   // 1.5 * 2^23: low mantissa bits of (x + magic) hold floor(x)
+  float2 r;
+  asm("add.rm.ftz.f32x2 %0, %1, %2;"
+      : "=l"(reinterpret_cast<uint64_t&>(r))
+      : "l"(reinterpret_cast<const uint64_t&>(x)), "l"(reinterpret_cast<const uint64_t&>(magic)));
+  const float2 nmagic = make_float2(-12582912.f, -12582912.f);
+  const float2 fl = fadd2(r, nmagic);                          // floor(x), exact
+  const float2 f = fadd2(x, make_float2(-fl.x, -fl.y));        // fractional part in [0, 1)
+  float2 p = ffma2(f, make_float2(0.0771186f, 0.0771186f), make_float2(0.2275957f, 0.2275957f));
+  p = ffma2(p, f, make_float2(0.6951786f, 0.6951786f));
+  p = ffma2(p, f, make_float2(1.f, 1.f));
+  p.x = __uint_as_float(__float_as_uint(p.x) + (__float_as_uint(r.x) << 23));   // multiply by 2^floor(x) through the exponent field
+  p.y = __uint_as_float(__float_as_uint(p.y) + (__float_as_uint(r.y) << 23));
+  return p;
 }
 __device__ __forceinline__ float silu(float x) { return x / (1.f + expf(-x)); }
 

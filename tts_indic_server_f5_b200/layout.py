@@ -25,7 +25,7 @@ class PackedLayout:
     half_rows: int              # R, multiple of 128
     row_pos: torch.Tensor       # int32 [2R]: position inside the utterance, -1 on gap rows (both halves)
     row_utt: torch.Tensor       # int32 [R]: utterance index, -1 on gap rows
-    attn_tiles: torch.Tensor    # int32 [T,4]: q_row0, kv_row0, kv_len, q_rows_valid (both halves)
+    attn_tiles: torch.Tensor    # int32 [T,4]: q_row0, kv_row0, kv_len, q_rows_valid (<= 256: a PAIR of 128-row tiles), both halves
     seg_rows: torch.Tensor      # int32 [2B,2]: row0, rows (both halves; GRN segments)
 
     @property
@@ -57,8 +57,8 @@ def build_layout(lengths: list[int], gap: int = GAP, both_halves: bool = True) -
     for off in halves:
         for s, n in zip(starts, lengths):
             segs.append([off + s, n])
-            for q0 in range(0, n, 128):
-                tiles.append([off + s + q0, off + s, n, min(128, n - q0)])
+            for q0 in range(0, n, 256):
+                tiles.append([off + s + q0, off + s, n, min(256, n - q0)])
     # longest-first ordering keeps the tail of the attention grid short
     tiles.sort(key=lambda t: -t[2])
     return PackedLayout(list(lengths), starts, R, torch.cat([pos] * len(halves)), utt,
