@@ -10,7 +10,7 @@ import sys
 
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
-LIB = os.path.join(PKG, "libf5b200.so")
+LIB = os.path.join(PKG, "libf5b200" + os.environ.get("F5_LIB_SUFFIX", "") + ".so")   # suffix: A/B builds of kernel variants
 SOURCES = ["gemm_tcgen05.cu", "attn_tcgen05.cu", "elementwise.cu", "vocos_istft.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
               "-Xcompiler", "-fPIC", "-cudart", "static"]
@@ -34,7 +34,7 @@ def is_stale() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not is_stale():
         return LIB
-    cmd = [_nvcc(), *NVCC_FLAGS, "-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    cmd = [_nvcc(), *NVCC_FLAGS, *os.environ.get("F5_NVCC_EXTRA", "").split(), "-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")

@@ -23,6 +23,9 @@ constexpr int ATT_TILE_BYTES = 128 * 64 * 2;  // 16 KB
 constexpr int ATT_KV_STAGES = 2;
 constexpr int ATT_SMEM = ATT_TILE_BYTES * (2 /*Q*/ + 2 * ATT_KV_STAGES /*K,V*/ + 8 /*P_A,P_B double-buffered*/) + 256;
 constexpr int ATT_TMEM_COLS = 512;
+#ifndef ATT_EXP_BF16X2
+#define ATT_EXP_BF16X2 0    // 1: ex2.approx.ftz.bf16x2 (two exponentials per MUFU op). Measured on B200 (tools/attn_bench.py): C2 1549 us vs 1426 us with fp32 exps — the extra unpack ALU work costs more than the MUFU ops it saves
+#endif
 #ifndef ATT_POLY_COUNT
 #define ATT_POLY_COUNT 0      // of every ATT_POLY_PERIOD score pairs, this many take the polynomial exp2 path (measured on B200: 25-50 % offload was NOT faster — the FMA/ALU pipes are already busy with scale, sum, max and bf16 packing)
 #endif
@@ -280,6 +283,13 @@ attn_d64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnParams p
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             float2 e = ffma2(make_float2(__uint_as_float(r[c * 32 + 2 * i]), __uint_as_float(r[c * 32 + 2 * i + 1])), sc2, nm2);
+#if ATT_EXP_BF16X2
+            // one MUFU op yields both exponentials, already in the bf16 the PV MMA consumes; the row sum is taken over the
+            // SAME rounded values (numerator and denominator stay consistent).
+            const uint32_t pb = ex2_bf16x2(pack_bf16x2(e.x, e.y));
+            pk[i] = pb;
+            ls2 = fadd2(ls2, make_float2(__uint_as_float(pb << 16), __uint_as_float(pb & 0xffff0000u)));
+#else
             if ((i % ATT_POLY_PERIOD) < ATT_POLY_COUNT) {   // this pair on the FMA/ALU pipes, the others on the MUFU
               e = exp2_poly2(e);
             } else {
@@ -288,6 +298,7 @@ attn_d64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnParams p
             }
             ls2 = fadd2(ls2, e);
             pk[i] = pack_bf16x2(e.x, e.y);
+#endif
           }
           uint8_t* blk = sPt + (c >> 1) * ATT_TILE_BYTES + row * 128;
 #pragma unroll
