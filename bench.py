@@ -112,6 +112,16 @@ def cpu_reference_leg(workload: str, nfe_sample: int, reps: int, warmup: int):
                       f"{statistics.mean(t[1] for t in times):.1f} s measured per sample"}, est
 
 
+def emit(line: dict) -> None:
+    """The ONE JSON line goes to the real stdout; everything else the process prints (NCCL banners, library chatter)
+    was re-routed to stderr at start-up."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -138,7 +148,7 @@ def main():
                            "sway": -1.0},
                 "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
-        print(json.dumps(line))
+        emit(line)
         return
 
     import torch.distributed as dist
@@ -279,7 +289,7 @@ def main():
         }
         if cpu_baseline is not None:
             line["cpu_baseline"] = cpu_baseline
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
