@@ -22,11 +22,13 @@ t0 = a[a > 0].min()
 prod = a[0][a[0] > 0] - t0
 print("producer kv-load issue times (first 24):", prod[:24].tolist())
 m = a[1][a[1] > 0] - t0
-print("MMA events (per iter: top, pA, issuedA, pB, issuedB) first 40:", m[:40].tolist())
+print("MMA events (per step: top, next QKs issued, PVs issued) first 45:", m[:45].tolist())
 for r in (2, 3):
-    s = a[r][:160].reshape(-1, 4)
+    s = a[r][:512].reshape(-1, 8)[:, :6]
     s = s[(s > 0).all(axis=1)] - t0
-    print(f"softmax group {r-2}: per tile [s_full seen, S loaded+max, o_full ok, arrived] first 12:")
-    for row in s[:12]: print("   ", row.tolist(), " softmax dur", int(row[3] - row[0]))
+    print(f"softmax group {r-2}: per tile [s_full seen, +S in regs, +max/grow, +o_full/readout/rescale, +exps, +st wait & p_full arrive | gap to next s_full] first 14:")
+    for k, row in enumerate(s[:14]):
+        nxt = int(s[k + 1][0] - row[5]) if k + 1 < len(s) else -1
+        print("   ", int(row[0]), np.diff(row).tolist(), "| gap", nxt, " total", int(row[5] - row[0]))
     d = np.diff(s[:, 0])
     print("   tile period (s_full to s_full):", d[:16].tolist())

@@ -1,33 +1,53 @@
 // Non-causal variable-length flash attention, head_dim 64, on tcgen05 (sm_100a).
 //
-// Persistent: one CTA per SM walks a list of work items = (pair of 128-row query tiles of one utterance, head).
-//   warp 0     : TMA producer  (Q pair once per item; K_j / V_j tiles of 128 keys through a 2-stage ring)
-//   warp 1     : MMA issuer    S_g = Q_g K_j^T (128x128x64, SS) -> TMEM;  O_g += P_g V_j (128x64x128, V as MN-major B operand
-//                              read straight from the QKV buffer — no transpose pass) -> TMEM           (g = tile A / tile B)
-//   warps 2-5  : softmax group A, warps 6-9: softmax group B — one thread per query row (= TMEM lane): row max, exp2 with
-//                packed FFMA2/FADD2, P_g as bf16 into a 128B-swizzled smem tile, lazy rescale of O_g in TMEM, final O/l store.
-// The two groups ping-pong on the SAME K/V tiles: while group A runs its exps (MUFU-bound: 16 k exps per tile vs 512 MMA
-// cycles) the tensor core works for group B and vice versa, so neither the MUFU nor the tensor pipe waits on the
-// softmax -> MMA -> softmax dependency chain of a single tile.  TMEM: S_A | S_B | O_A | O_B = 384 of 512 columns.
+// Persistent: one CTA per SM walks a list of work items = (pair of 128-row query tiles of one utterance, head).  The
+// (item, key tile) pairs form ONE flat sequence of steps s = 0, 1, 2, ... that every role walks in the same order:
+//   warp 8     : TMA producer  (Q pair once per item; K_s and V_s tiles of 128 keys through two SEPARATE 3-stage rings:
+//                              K_{s+1} is consumed a whole softmax earlier than V_s)
+//   warp 9     : MMA issuer    S_g = Q_g K_s^T (128x128x64, SS) -> TMEM;  O_g += P_g V_s (128x64x128, TS: P_g is the A operand
+//                              IN TMEM, V the MN-major B operand read straight from the QKV buffer's tile — no transpose)
+//   warps 0-3  : softmax group A, warps 4-7: softmax group B (g = query tile A / B) — one thread per query row (= TMEM
+//                lane): S row read ONCE into registers, row max, exp2 with packed FFMA2/FADD2, P_g as packed bf16 back into
+//                TMEM (tcgen05.st), lazy rescale of O_g in TMEM, final O/l store.
+// Why P lives in TMEM: per step the SS form moved 256 KB through shared memory (QK operands 64 KB, PV operands 96 KB,
+// P stores 64 KB, TMA fills 32 KB) = 2048 cycles at 128 B/clk — more than the 1024 tensor cycles and as much as the MUFU's
+// 2048 (16 k exps per tile at 16/clk).  With P in TMEM the shared-memory traffic halves and the MUFU is the only unit near
+// its limit.
+// Software pipeline (what keeps the MUFU busy):
+//   * a softmax thread releases S_g (`s_free`) as soon as its row sits in registers, so QK_g(s+1) is issued at the START
+//     of softmax_g(s) and S_g(s+1) is waiting in TMEM when softmax_g(s) ends — no QK round trip between tiles;
+//   * the step sequence is flat across work items: the first QK of the next item is issued during the last softmax of the
+//     current one (Q is refilled as soon as the item's last QK retired);
+//   * the O/l read-out of item i is deferred into the first softmax of item i+1 (after its row max, before its first P
+//     store), so the last PV's latency is hidden behind the S load and the max pass;
+//   * the two groups are kept HALF A TILE APART: QK_B(s) is only issued once group A has finished the row max of its
+//     tile s (`a_gate`), so B's TMEM load + max pass (no MUFU work) overlaps A's exponentials and vice versa.  Left alone
+//     the groups drift into lockstep (measured: both idle the MUFU for ~1100 of 3400 cycles per tile).
+//     MMA issue order per step a:  QK_A(a+1) | QK_B(a) | PV_B(a-1) | PV_A(a).
+// TMEM: S_A | S_B | P_A | P_B | O_A | O_B = 128+128+64+64+64+64 = 512 columns.
 #include "f5_common.cuh"
 #include "../../include/f5_b200.h"
 #include <cstdlib>
 
 namespace f5 {
 
-constexpr int ATT_THREADS = 320;
+constexpr int ATT_THREADS = 384;   // warpgroup 0 / 1: softmax groups A / B; warpgroup 2: producer, MMA issuer, 2 idle warps
 constexpr int ATT_BM = 128;   // query rows per tile (two tiles per work item)
 constexpr int ATT_BN = 128;   // keys per tile
 constexpr int ATT_D = 64;
 constexpr int ATT_TILE_BYTES = 128 * 64 * 2;  // 16 KB
-constexpr int ATT_KV_STAGES = 2;
-constexpr int ATT_SMEM = ATT_TILE_BYTES * (2 /*Q*/ + 2 * ATT_KV_STAGES /*K,V*/ + 8 /*P_A,P_B double-buffered*/) + 256;
+constexpr int ATT_KV_STAGES = 3;
+constexpr int ATT_SMEM = ATT_TILE_BYTES * (2 /*Q*/ + 2 * ATT_KV_STAGES /*K,V*/) + 256;
 constexpr int ATT_TMEM_COLS = 512;
+constexpr uint32_t ATT_TM_S = 0, ATT_TM_P = 256, ATT_TM_O = 384;   // column offsets; per group: + g*128 / g*64 / g*64
 #ifndef ATT_EXP_BF16X2
-#define ATT_EXP_BF16X2 0    // 1: ex2.approx.ftz.bf16x2 (two exponentials per MUFU op). Measured on B200 (tools/attn_bench.py): C2 1549 us vs 1426 us with fp32 exps — the extra unpack ALU work costs more than the MUFU ops it saves
+#define ATT_EXP_BF16X2 0    // 1: ex2.approx.ftz.bf16x2 (two exponentials per MUFU op); A/B switch, see tools/attn_bench.py
 #endif
 #ifndef ATT_POLY_COUNT
-#define ATT_POLY_COUNT 0      // of every ATT_POLY_PERIOD score pairs, this many take the polynomial exp2 path (measured on B200: 25-50 % offload was NOT faster — the FMA/ALU pipes are already busy with scale, sum, max and bf16 packing)
+#define ATT_POLY_COUNT 0      // of every ATT_POLY_PERIOD score pairs, this many take the polynomial exp2 path (FMA pipes) instead of the MUFU
+#endif
+#ifndef ATT_EXP_PIPE
+#define ATT_EXP_PIPE 0
 #endif
 #ifndef ATT_POLY_PERIOD
 #define ATT_POLY_PERIOD 4
@@ -69,6 +89,32 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr) {
 
 #define F5_TRACE(role, idx) do { if (p.trace != nullptr && blockIdx.x == 0 && (idx) < 512) p.trace[(role) * 512 + (idx)] = clock64(); } while (0)
 
+// Walks the CTA's flat step sequence: work items w = blockIdx.x, +gridDim.x, ...; key tiles j = 0..nkv-1 inside each.
+struct StepWalker {
+  const int* items;
+  int num_work, heads;
+  int w, j, nkv, ngroups, head;
+  int4 it;
+  __device__ __forceinline__ explicit StepWalker(const AttnParams& p)
+      : items(p.items), num_work(p.num_work), heads(p.heads), w(static_cast<int>(blockIdx.x)), j(0) { load(); }
+  __device__ __forceinline__ bool valid() const { return w < num_work; }
+  __device__ __forceinline__ void load() {
+    if (w < num_work) {
+      it = *reinterpret_cast<const int4*>(items + 4 * (w / heads));
+      head = w % heads;
+      nkv = (it.z + ATT_BN - 1) / ATT_BN;
+      ngroups = it.w > ATT_BM ? 2 : 1;
+    }
+  }
+  __device__ __forceinline__ bool last_tile() const { return j + 1 == nkv; }
+  __device__ __forceinline__ void next() {
+    if (++j == nkv) { j = 0; w += static_cast<int>(gridDim.x); load(); }
+  }
+};
+
+// Registers: the file is 16 K per SM sub-partition and every sub-partition hosts one warp of each warpgroup, so a flat
+// allocation caps at 168/thread — not enough for the 128-register S row plus the exp pipeline.  setmaxnreg moves
+// registers from the producer/MMA warpgroup (72) to the two softmax warpgroups (216): 2 x 216 + 72 = 504 <= 512 = 16 K / 32 (an exact 512 never gets its registers: the inc hangs).
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attn_d64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -76,35 +122,41 @@ attn_d64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnParams p
   uint8_t* sQ = smem;                                         // [2] tiles A, B
   uint8_t* sK = sQ + 2 * ATT_TILE_BYTES;                      // [ATT_KV_STAGES]
   uint8_t* sV = sK + ATT_KV_STAGES * ATT_TILE_BYTES;          // [ATT_KV_STAGES]
-  uint8_t* sP = sV + ATT_KV_STAGES * ATT_TILE_BYTES;          // [2 groups][2 buffers][2 K-atom blocks of 16 KB]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 8 * ATT_TILE_BYTES);
-  uint64_t* q_full = bars;          // 1
-  uint64_t* q_empty = bars + 1;     // 1
-  uint64_t* kv_full = bars + 2;     // [ATT_KV_STAGES <= 3]
-  uint64_t* kv_empty = bars + 5;    // [ATT_KV_STAGES <= 3]
-  uint64_t* s_full = bars + 8;      // [2]
-  uint64_t* p_full = bars + 10;     // [2]
-  uint64_t* o_full = bars + 12;     // [2]
-  uint64_t* o_free = bars + 14;     // [2]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 16);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + ATT_KV_STAGES * ATT_TILE_BYTES);
+  uint64_t* q_full = bars;          // [2 groups]
+  uint64_t* q_empty = bars + 2;     // [2 groups]
+  uint64_t* k_full = bars + 4;      // [ATT_KV_STAGES <= 4]
+  uint64_t* k_empty = bars + 8;
+  uint64_t* v_full = bars + 12;
+  uint64_t* v_empty = bars + 16;
+  uint64_t* s_full = bars + 20;     // [2 groups]
+  uint64_t* s_free = bars + 22;
+  uint64_t* p_full = bars + 24;
+  uint64_t* o_full = bars + 26;
+  uint64_t* a_gate = bars + 28;     // group A finished the row max of its tile
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 29);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tmap_qkv);
-    mbar_init(q_full, 1);
-    mbar_init(q_empty, 1);
-    for (int i = 0; i < ATT_KV_STAGES; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+    mbar_init(a_gate, 128);
+    for (int i = 0; i < ATT_KV_STAGES; ++i) {
+      mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
+    }
     for (int g = 0; g < 2; ++g) {
+      mbar_init(&q_full[g], 1);
+      mbar_init(&q_empty[g], 1);
       mbar_init(&s_full[g], 1);
+      mbar_init(&s_free[g], 128);
       mbar_init(&p_full[g], 128);
       mbar_init(&o_full[g], 1);
-      mbar_init(&o_free[g], 128);
     }
     mbar_fence_init();
   }
-  if (warp == 1) {
+  if (warp == 9) {
     tmem_alloc(tmem_ptr, ATT_TMEM_COLS);
     tmem_relinquish();
   }
@@ -113,124 +165,163 @@ attn_d64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnParams p
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  if (warp == 0) {
+  if (warp >= 8) {
+   asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
+   if (warp == 8) {
     // ------------------------------------------------------------------ TMA producer
+    // Issue order per step s:  Q_A(item) | K(s) | Q_B(item) | V(s-1)  — the order the MMA warp consumes them in.
     if (lane == 0) {
-      uint32_t item = 0, g_kv = 0;
-      for (int w = blockIdx.x; w < p.num_work; w += gridDim.x, ++item) {
-        const int4 it = *reinterpret_cast<const int4*>(p.items + 4 * (w / p.heads));
-        const int head = w % p.heads;
-        const int nkv = (it.z + ATT_BN - 1) / ATT_BN;
-        mbar_wait(q_empty, (item & 1) ^ 1);                    // previous item's last QK has retired
-        mbar_expect_tx(q_full, (it.w > ATT_BM ? 2 : 1) * ATT_TILE_BYTES);
-        tma_load_2d(sQ, &tmap_qkv, q_full, p.q_col + head * ATT_D, it.x);
-        if (it.w > ATT_BM) tma_load_2d(sQ + ATT_TILE_BYTES, &tmap_qkv, q_full, p.q_col + head * ATT_D, it.x + ATT_BM);
-        for (int j = 0; j < nkv; ++j, ++g_kv) {
-          const uint32_t st = g_kv % ATT_KV_STAGES, ph = (g_kv / ATT_KV_STAGES) & 1;
-          mbar_wait(&kv_empty[st], ph ^ 1);
-          mbar_expect_tx(&kv_full[st], 2 * ATT_TILE_BYTES);
-          tma_load_2d(sK + st * ATT_TILE_BYTES, &tmap_qkv, &kv_full[st], p.k_col + head * ATT_D, it.y + j * ATT_BN);
-          tma_load_2d(sV + st * ATT_TILE_BYTES, &tmap_qkv, &kv_full[st], p.v_col + head * ATT_D, it.y + j * ATT_BN);
-          F5_TRACE(0, g_kv);
+      uint32_t item_a = 0, item_b = 0, s = 0;
+      int v_col = 0, v_row = 0;
+      auto load_v = [&](uint32_t sv_step) {
+        const uint32_t sv = sv_step % ATT_KV_STAGES, pv = (sv_step / ATT_KV_STAGES) & 1;
+        mbar_wait(&v_empty[sv], pv ^ 1);
+        mbar_expect_tx(&v_full[sv], ATT_TILE_BYTES);
+        tma_load_2d(sV + sv * ATT_TILE_BYTES, &tmap_qkv, &v_full[sv], v_col, v_row);
+      };
+      for (StepWalker c(p); c.valid(); c.next(), ++s) {
+        if (c.j == 0) {
+          mbar_wait(&q_empty[0], (item_a & 1) ^ 1);            // previous item's last QK_A has retired
+          mbar_expect_tx(&q_full[0], ATT_TILE_BYTES);
+          tma_load_2d(sQ, &tmap_qkv, &q_full[0], p.q_col + c.head * ATT_D, c.it.x);
+          ++item_a;
         }
+        const uint32_t st = s % ATT_KV_STAGES, ph = (s / ATT_KV_STAGES) & 1;
+        mbar_wait(&k_empty[st], ph ^ 1);
+        mbar_expect_tx(&k_full[st], ATT_TILE_BYTES);
+        tma_load_2d(sK + st * ATT_TILE_BYTES, &tmap_qkv, &k_full[st], p.k_col + c.head * ATT_D, c.it.y + c.j * ATT_BN);
+        F5_TRACE(0, s);
+        if (c.j == 0 && c.ngroups == 2) {
+          mbar_wait(&q_empty[1], (item_b & 1) ^ 1);            // group B's previous item's last QK_B has retired
+          mbar_expect_tx(&q_full[1], ATT_TILE_BYTES);
+          tma_load_2d(sQ + ATT_TILE_BYTES, &tmap_qkv, &q_full[1], p.q_col + c.head * ATT_D, c.it.x + ATT_BM);
+          ++item_b;
+        }
+        if (s > 0) load_v(s - 1);
+        v_col = p.v_col + c.head * ATT_D;
+        v_row = c.it.y + c.j * ATT_BN;
       }
+      if (s > 0) load_v(s - 1);
     }
-  } else if (warp == 1) {
+   } else if (warp == 9) {
     // ------------------------------------------------------------------ MMA issuer
     // The WHOLE warp walks the loop (warp-uniform control flow keeps descriptors / addresses in uniform registers, which is
     // what UTCHMMA consumes); only the tcgen05.mma / commit instructions themselves are predicated on one elected lane.
-    // Issuing from inside a divergent `if (lane == 0)` region costs a serial R2UR chain per MMA (~85 cycles each, measured),
-    // which made 24 MMAs per tile pair slower than the tensor work they describe.
-    {
-      constexpr uint32_t idesc_qk = umma_idesc_bf16(ATT_BM, ATT_BN);
-      constexpr uint32_t idesc_pv = umma_idesc_bf16(ATT_BM, ATT_D) | (1u << 16);   // B (= V) is MN-major
-      const bool leader = elect_one();
-      const uint64_t qd0 = umma_desc_k_sw128(smem_u32(sQ));
-      const uint64_t kd0 = umma_desc_k_sw128(smem_u32(sK));
-      const uint64_t pd0 = umma_desc_k_sw128(smem_u32(sP));
-      const uint64_t vd0 = umma_desc_mn_sw128(smem_u32(sV));
-      constexpr uint64_t TILE16 = ATT_TILE_BYTES >> 4;      // descriptor address field is in 16-B units
-      uint32_t item = 0, g_kv = 0, ev = 0;
-      uint32_t t[2] = {0, 0};        // tiles processed so far per group (phase of s_full / p_full / o_full)
-      uint32_t it_g[2] = {0, 0};     // items processed so far per group (phase of o_free)
-      auto issue_qk = [&](int g, uint32_t st) {
-        const uint64_t qd = qd0 + g * TILE16, kd = kd0 + st * TILE16;
-        if (leader) {
+    constexpr uint32_t idesc_qk = umma_idesc_bf16(ATT_BM, ATT_BN);
+    constexpr uint32_t idesc_pv = umma_idesc_bf16(ATT_BM, ATT_D) | (1u << 16);   // A (= P, TMEM) K-major; B (= V) MN-major
+    const bool leader = elect_one();
+    const uint64_t qd0 = umma_desc_k_sw128(smem_u32(sQ));
+    const uint64_t kd0 = umma_desc_k_sw128(smem_u32(sK));
+    const uint64_t vd0 = umma_desc_mn_sw128(smem_u32(sV));
+    constexpr uint64_t TILE16 = ATT_TILE_BYTES >> 4;      // descriptor address field is in 16-B units
+    uint32_t a = 0, ev = 0;
+    uint32_t iq0 = 0, iq1 = 0;     // items started per group (phase of q_full)
+    uint32_t tq0 = 0, tq1 = 0;     // QKs issued so far per group (phase of s_free)
+    uint32_t tp0 = 0, tp1 = 0;     // PVs issued so far per group (phase of p_full)
+    // S_g(step) = Q_g K^T: waits for the group's previous S to be in registers, then 4 MMAs + commit
+    auto issue_qk = [&](int g, const StepWalker& c, uint32_t step, uint32_t& iq, uint32_t& tq) {
+      const uint32_t st = step % ATT_KV_STAGES;
+      if (c.j == 0) { mbar_wait(&q_full[g], iq & 1); ++iq; }
+      mbar_wait(&k_full[st], (step / ATT_KV_STAGES) & 1);
+      if (tq > 0) mbar_wait(&s_free[g], (tq - 1) & 1);
+      tc_fence_after();
+      const uint64_t qd = qd0 + g * TILE16, kd = kd0 + st * TILE16;
+      if (leader) {
 #pragma unroll
-          for (int kk = 0; kk < ATT_D / 16; ++kk)
-            umma_f16_ss(tmem_base + g * ATT_BN, qd + 2 * kk, kd + 2 * kk, idesc_qk, kk != 0);
-          umma_commit(&s_full[g]);
-        }
-        __syncwarp();
-      };
-      auto issue_pv = [&](int g, uint32_t st, bool first) {
-        const uint64_t pd = pd0 + (g * 4 + (t[g] & 1) * 2) * TILE16, vd = vd0 + st * TILE16;
-        if (leader) {
-#pragma unroll
-          for (int kk = 0; kk < ATT_BN / 16; ++kk)            // 16 keys = 2 KB (128 x 16 B) of the V tile per MMA
-            umma_f16_ss(tmem_base + 2 * ATT_BN + g * ATT_D, pd + (kk >> 2) * TILE16 + 2 * (kk & 3), vd + kk * 128, idesc_pv,
-                        (!first || kk != 0) ? 1u : 0u);
-          umma_commit(&o_full[g]);
-        }
-        __syncwarp();
-      };
-      for (int w = blockIdx.x; w < p.num_work; w += gridDim.x, ++item) {
-        const int4 it = *reinterpret_cast<const int4*>(p.items + 4 * (w / p.heads));
-        const int nkv = (it.z + ATT_BN - 1) / ATT_BN;
-        const int ngroups = it.w > ATT_BM ? 2 : 1;
-        mbar_wait(q_full, item & 1);
-        {
-          const uint32_t st = g_kv % ATT_KV_STAGES, ph = (g_kv / ATT_KV_STAGES) & 1;
-          mbar_wait(&kv_full[st], ph);
-          tc_fence_after();
-          for (int g = 0; g < ngroups; ++g) issue_qk(g, st);
-          if (nkv == 1 && leader) umma_commit(q_empty);      // every QK of this item is issued: the Q tiles may be refilled
-        }
-        for (int j = 0; j < nkv; ++j, ++g_kv) {
-          const uint32_t st = g_kv % ATT_KV_STAGES;
-          const bool more = j + 1 < nkv;
-          uint32_t stn = 0;
-          if (more) {
-            stn = (g_kv + 1) % ATT_KV_STAGES;
-            mbar_wait(&kv_full[stn], ((g_kv + 1) / ATT_KV_STAGES) & 1);
-          }
-          if (lane == 0) { F5_TRACE(1, ev); }
-          ++ev;
-          for (int g = 0; g < ngroups; ++g) {
-            mbar_wait(&p_full[g], t[g] & 1);       // group g consumed S_g(j) and wrote P_g(j)
-            tc_fence_after();
-            if (lane == 0) { F5_TRACE(1, ev); }
-            ++ev;
-            if (more) issue_qk(g, stn);            // S_g is free again: next scores first, so group g never waits on its own PV
-            if (j == 0) {                          // O_g of the previous item must have been read out
-              mbar_wait(&o_free[g], (it_g[g] & 1) ^ 1);
-              tc_fence_after();
-            }
-            issue_pv(g, st, j == 0);
-            if (lane == 0) { F5_TRACE(1, ev); }
-            ++ev;
-            ++t[g];
-          }
-          if (leader) {
-            umma_commit(&kv_empty[st]);              // both groups' PV on (K_j, V_j) retired -> stage reusable
-            if (more && j + 2 == nkv) umma_commit(q_empty);   // the last tile's QKs were just issued: next item's Q may load
-          }
-          __syncwarp();
-        }
-        for (int g = 0; g < ngroups; ++g) ++it_g[g];
+        for (int kk = 0; kk < ATT_D / 16; ++kk)
+          umma_f16_ss(tmem_base + ATT_TM_S + g * ATT_BN, qd + 2 * kk, kd + 2 * kk, idesc_qk, kk != 0);
+        umma_commit(&s_full[g]);
+        if (c.last_tile()) umma_commit(&q_empty[g]);   // every QK_g of the item is issued: Q_g may be refilled
       }
+      __syncwarp();
+      ++tq;
+    };
+    // O_g (+)= P_g V: P_g from TMEM (8 columns = 16 bf16 keys per MMA), V tile rows kk*16.. (2 KB per MMA)
+    auto issue_pv = [&](int g, const StepWalker& c, uint32_t step, uint32_t& tp) {
+      const uint32_t st = step % ATT_KV_STAGES;
+      mbar_wait(&v_full[st], (step / ATT_KV_STAGES) & 1);
+      mbar_wait(&p_full[g], tp & 1);                // group g wrote P_g (and read out the previous item's O_g if j == 0)
+      tc_fence_after();
+      const uint64_t vd = vd0 + st * TILE16;
+      const bool first = c.j == 0;
+      if (leader) {
+#pragma unroll
+        for (int kk = 0; kk < ATT_BN / 16; ++kk)
+          umma_f16_ts(tmem_base + ATT_TM_O + g * ATT_D, tmem_base + ATT_TM_P + g * (ATT_BN / 2) + kk * 8, vd + kk * 128,
+                      idesc_pv, (!first || kk != 0) ? 1u : 0u);
+        umma_commit(&o_full[g]);
+      }
+      __syncwarp();
+      ++tp;
+    };
+    StepWalker cur(p), prv(p), nxt(p);
+    nxt.next();
+    if (cur.valid()) issue_qk(0, cur, 0, iq0, tq0);
+    while (cur.valid()) {
+      if (lane == 0) { F5_TRACE(1, ev); }
+      ++ev;
+      if (nxt.valid()) issue_qk(0, nxt, a + 1, iq0, tq0);          // QK_A(a+1): at the start of softmax_A(a)
+      mbar_wait(a_gate, a & 1);                                    // softmax_A(a) is past its row max
+      if (cur.ngroups == 2) issue_qk(1, cur, a, iq1, tq1);         // QK_B(a): group B runs half a tile behind A
+      if (leader) umma_commit(&k_empty[a % ATT_KV_STAGES]);        // QK_A(a) (issued a step ago) and QK_B(a) retired -> K stage reusable
+      __syncwarp();
+      if (lane == 0) { F5_TRACE(1, ev); }
+      ++ev;
+      if (a > 0) {
+        if (prv.ngroups == 2) issue_pv(1, prv, a - 1, tp1);        // PV_B(a-1)
+        if (leader) umma_commit(&v_empty[(a - 1) % ATT_KV_STAGES]);
+        __syncwarp();
+      }
+      issue_pv(0, cur, a, tp0);                                    // PV_A(a)
+      if (lane == 0) { F5_TRACE(1, ev); }
+      ++ev;
+      prv = cur;
+      cur = nxt;
+      nxt.next();
+      ++a;
     }
+    if (a > 0) {
+      if (prv.ngroups == 2) issue_pv(1, prv, a - 1, tp1);
+      if (leader) umma_commit(&v_empty[(a - 1) % ATT_KV_STAGES]);
+      __syncwarp();
+    }
+   }
   } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
     // ------------------------------------------------------------------ softmax groups
-    const int g = (warp - 2) >> 2;                // 0: tile A, 1: tile B
+    const int g = warp >> 2;                      // 0: tile A, 1: tile B
     const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
     const int row = quarter * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
-    const uint32_t tmem_S = tmem_base + g * ATT_BN;
-    const uint32_t tmem_O = tmem_base + 2 * ATT_BN + g * ATT_D;
-    uint8_t* sPg = sP + g * 4 * ATT_TILE_BYTES;
+    const uint32_t tmem_S = tmem_base + ATT_TM_S + g * ATT_BN + lane_off;
+    const uint32_t tmem_P = tmem_base + ATT_TM_P + g * (ATT_BN / 2) + lane_off;
+    const uint32_t tmem_O = tmem_base + ATT_TM_O + g * ATT_D + lane_off;
     const float2 sc2 = make_float2(p.scale_log2, p.scale_log2);
     uint32_t t = 0;
+    // deferred read-out of the previous item's O (runs inside the first softmax of the next item)
+    bool pend = false;
+    float pend_inv_l = 0.f;
+    __nv_bfloat16* pend_out = nullptr;            // nullptr: row beyond q_valid, nothing to store
+    auto read_out = [&]() {
+#pragma unroll 1
+      for (int c = 0; c < ATT_D / 32; ++c) {
+        uint32_t ro[32];
+        tmem_ld_32x32b_x32(tmem_O + c * 32, ro);
+        tmem_ld_wait();
+        if (pend_out != nullptr) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) {
+            uint4 wv;
+            wv.x = pack_bf16x2(__uint_as_float(ro[i]) * pend_inv_l, __uint_as_float(ro[i + 1]) * pend_inv_l);
+            wv.y = pack_bf16x2(__uint_as_float(ro[i + 2]) * pend_inv_l, __uint_as_float(ro[i + 3]) * pend_inv_l);
+            wv.z = pack_bf16x2(__uint_as_float(ro[i + 4]) * pend_inv_l, __uint_as_float(ro[i + 5]) * pend_inv_l);
+            wv.w = pack_bf16x2(__uint_as_float(ro[i + 6]) * pend_inv_l, __uint_as_float(ro[i + 7]) * pend_inv_l);
+            *reinterpret_cast<uint4*>(pend_out + c * 32 + i) = wv;
+          }
+        }
+      }
+      pend = false;
+    };
     for (int w = blockIdx.x; w < p.num_work; w += gridDim.x) {
       const int4 it = *reinterpret_cast<const int4*>(p.items + 4 * (w / p.heads));
       const int head = w % p.heads;
@@ -244,23 +335,29 @@ attn_d64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnParams p
         const bool full = kv_valid == ATT_BN;     // only the last tile of an utterance needs key masking
         mbar_wait(&s_full[g], t & 1);
         tc_fence_after();
-        if (row == 0) F5_TRACE(2 + g, 4 * t);
-        // S row (128 fp32) is read from TMEM ONCE into registers: LDTM bandwidth, not MUFU, limited the two-pass version.
+        if (row == 0) F5_TRACE(2 + g, 8 * t);
+        // S row (128 fp32) is read from TMEM ONCE into registers, then S_g is handed back to the MMA warp at once.
         uint32_t r[128];
-        tmem_ld_32x32b_x32(tmem_S + lane_off, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
-        tmem_ld_32x32b_x32(tmem_S + lane_off + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
-        tmem_ld_32x32b_x32(tmem_S + lane_off + 64, *reinterpret_cast<uint32_t(*)[32]>(&r[64]));
-        tmem_ld_32x32b_x32(tmem_S + lane_off + 96, *reinterpret_cast<uint32_t(*)[32]>(&r[96]));
+        tmem_ld_32x32b_x32(tmem_S, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
+        tmem_ld_32x32b_x32(tmem_S + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
+        tmem_ld_32x32b_x32(tmem_S + 64, *reinterpret_cast<uint32_t(*)[32]>(&r[64]));
+        tmem_ld_32x32b_x32(tmem_S + 96, *reinterpret_cast<uint32_t(*)[32]>(&r[96]));
         tmem_ld_wait();
+        if (row == 0) F5_TRACE(2 + g, 8 * t + 1);
+        tc_fence_before();
+        mbar_arrive(&s_free[g]);
         if (!full) {
 #pragma unroll
           for (int i = 0; i < 128; ++i)
             if (i >= kv_valid) r[i] = 0xff800000u;   // -inf: masked keys drop out of the max and give exp2 = 0
         }
-        float mx = -INFINITY;
+        // row max as 8 independent chains (a single 64-deep FMNMX chain cost ~550 cycles of pure latency per tile)
+        float mxs[8];
 #pragma unroll
-        for (int i = 0; i < 64; ++i) mx = fmaxf(mx, fmaxf(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])));
-        if (row == 0) F5_TRACE(2 + g, 4 * t + 1);
+        for (int k = 0; k < 8; ++k) mxs[k] = fmaxf(__uint_as_float(r[2 * k]), __uint_as_float(r[2 * k + 1]));
+#pragma unroll
+        for (int i = 8; i < 64; ++i) mxs[i & 7] = fmaxf(mxs[i & 7], fmaxf(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])));
+        const float mx = fmaxf(fmaxf(fmaxf(mxs[0], mxs[1]), fmaxf(mxs[2], mxs[3])), fmaxf(fmaxf(mxs[4], mxs[5]), fmaxf(mxs[6], mxs[7])));
         // lazy rescale: keep a stale running max while it is within 2^8 of the true one (p <= 256 is harmless in bf16/fp32);
         // O and l are only rescaled when the max really moved.  The first tile always "grows" (m_run = -inf, alpha = 0).
         const float m_new = fmaxf(m_run, mx * p.scale_log2);
@@ -271,12 +368,69 @@ attn_d64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnParams p
           alpha = fast_ex2(m_run - m_new);
           m_run = m_new;
         }
-        // p = exp2(s*scale - m), row sum, bf16 P -> swizzled smem.  P_g is double-buffered: the buffer written for tile t was
-        // last read by PV_g(t-2), which retired before QK_g(t) (in-order tensor pipe) — no wait on the previous PV needed.
-        if (row == 0) F5_TRACE(2 + g, 4 * t + 2);
+        if (g == 0) mbar_arrive(a_gate);          // group B's scores for this step may be issued now (half-tile stagger)
+        if (row == 0) F5_TRACE(2 + g, 8 * t + 2);
+        // The group's previous PV (issued at the end of the previous softmax) has normally retired by now.  It must have:
+        // it reads P_g (overwritten below) and accumulates into O_g (rescaled / read out below).  Waiting for it on EVERY
+        // tile also keeps this thread exactly one phase behind o_full (a parity wait must never fall two phases behind).
+        if (t > 0) {
+          mbar_wait(&o_full[g], (t - 1) & 1);
+          tc_fence_after();
+        }
+        if (pend) read_out();                     // previous item's O / l -> bf16 output rows, before PV(this item, 0) overwrites O_g
+        if (j > 0 && any_grow) {
+#pragma unroll 1
+          for (int c = 0; c < ATT_D / 32; ++c) {
+            uint32_t ro[32];
+            tmem_ld_32x32b_x32(tmem_O + c * 32, ro);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) ro[i] = __float_as_uint(__uint_as_float(ro[i]) * alpha);
+            tmem_st_32x32b_x32(tmem_O + c * 32, ro);
+          }
+        }
+        if (row == 0) F5_TRACE(2 + g, 8 * t + 3);
+        // p = exp2(s*scale - m), row sum, P as packed bf16 pairs -> TMEM columns [c*16, c*16+16) of P_g
         const float2 nm2 = make_float2(-m_run, -m_run);
         float2 ls2 = make_float2(0.f, 0.f);
-        uint8_t* sPt = sPg + (t & 1) * 2 * ATT_TILE_BYTES;
+#if ATT_EXP_PIPE
+        // Software pipeline over 32-key chunks: the exponentials of chunk c are issued before the sums / bf16 packing /
+        // TMEM store of chunk c-1, so no consumer sits within the MUFU's latency of its producer (one warp per
+        // sub-partition is in this phase at a time — there is no second warp to hide that latency).
+        float2 ls2b = make_float2(0.f, 0.f);
+        auto exps = [&](int c) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float2 e = ffma2(make_float2(__uint_as_float(r[c * 32 + 2 * i]), __uint_as_float(r[c * 32 + 2 * i + 1])), sc2, nm2);
+            if ((i % ATT_POLY_PERIOD) < ATT_POLY_COUNT) {
+              e = exp2_poly2(e);
+            } else {
+              e.x = fast_ex2(e.x);
+              e.y = fast_ex2(e.y);
+            }
+            r[c * 32 + 2 * i] = __float_as_uint(e.x);
+            r[c * 32 + 2 * i + 1] = __float_as_uint(e.y);
+          }
+        };
+        auto consume = [&](int c) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float2 e = make_float2(__uint_as_float(r[c * 32 + 2 * i]), __uint_as_float(r[c * 32 + 2 * i + 1]));
+            if (i & 1) ls2b = fadd2(ls2b, e); else ls2 = fadd2(ls2, e);
+            pk[i] = pack_bf16x2(e.x, e.y);
+          }
+          tmem_st_32x32b_x16(tmem_P + c * 16, pk);
+        };
+        exps(0);
+#pragma unroll
+        for (int c = 1; c < ATT_BN / 32; ++c) {
+          exps(c);
+          consume(c - 1);
+        }
+        consume(ATT_BN / 32 - 1);
+        ls2 = fadd2(ls2, ls2b);
+#else
 #pragma unroll
         for (int c = 0; c < ATT_BN / 32; ++c) {
           uint32_t pk[16];
@@ -300,63 +454,30 @@ attn_d64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnParams p
             pk[i] = pack_bf16x2(e.x, e.y);
 #endif
           }
-          uint8_t* blk = sPt + (c >> 1) * ATT_TILE_BYTES + row * 128;
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int chunk = (c & 1) * 4 + q;
-            *reinterpret_cast<uint4*>(blk + ((chunk ^ (row & 7)) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
-          }
+          tmem_st_32x32b_x16(tmem_P + c * 16, pk);
         }
+#endif
         l_run = l_run * alpha + (ls2.x + ls2.y);
-        if (j > 0 && any_grow) {
-          mbar_wait(&o_full[g], (t - 1) & 1);     // the previous PV of this group must have retired before O is rescaled
-          tc_fence_after();
-#pragma unroll 1
-          for (int c = 0; c < ATT_D / 32; ++c) {
-            uint32_t ro[32];
-            tmem_ld_32x32b_x32(tmem_O + lane_off + c * 32, ro);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) ro[i] = __float_as_uint(__uint_as_float(ro[i]) * alpha);
-            tmem_st_32x32b_x32(tmem_O + lane_off + c * 32, ro);
-          }
-          tmem_st_wait();
-        }
-        fence_proxy_async_smem();
+        if (row == 0) F5_TRACE(2 + g, 8 * t + 4);
+        tmem_st_wait();
         tc_fence_before();
         mbar_arrive(&p_full[g]);
-        if (row == 0) F5_TRACE(2 + g, 4 * t + 3);
+        if (row == 0) F5_TRACE(2 + g, 8 * t + 5);
       }
-      // epilogue of the item: O / l -> bf16 rows of the output
+      pend = true;
+      pend_inv_l = 1.f / l_run;
+      pend_out = row < q_valid ? p.out + static_cast<size_t>(it.x + g * ATT_BM + row) * p.ldo + head * ATT_D : nullptr;
+    }
+    if (pend) {
       mbar_wait(&o_full[g], (t - 1) & 1);
       tc_fence_after();
-      const float inv_l = 1.f / l_run;
-#pragma unroll 1
-      for (int c = 0; c < ATT_D / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(tmem_O + lane_off + c * 32, r);
-        tmem_ld_wait();
-        if (row < q_valid) {
-          __nv_bfloat16* o = p.out + static_cast<size_t>(it.x + g * ATT_BM + row) * p.ldo + head * ATT_D + c * 32;
-#pragma unroll
-          for (int i = 0; i < 32; i += 8) {
-            uint4 wv;
-            wv.x = pack_bf16x2(__uint_as_float(r[i]) * inv_l, __uint_as_float(r[i + 1]) * inv_l);
-            wv.y = pack_bf16x2(__uint_as_float(r[i + 2]) * inv_l, __uint_as_float(r[i + 3]) * inv_l);
-            wv.z = pack_bf16x2(__uint_as_float(r[i + 4]) * inv_l, __uint_as_float(r[i + 5]) * inv_l);
-            wv.w = pack_bf16x2(__uint_as_float(r[i + 6]) * inv_l, __uint_as_float(r[i + 7]) * inv_l);
-            *reinterpret_cast<uint4*>(o + i) = wv;
-          }
-        }
-      }
-      tc_fence_before();
-      mbar_arrive(&o_free[g]);                    // O_g may be overwritten by the next item's first PV
+      read_out();
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == 9) {
     tc_fence_after();
     tmem_dealloc(tmem_base, ATT_TMEM_COLS);
   }
