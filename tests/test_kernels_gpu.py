@@ -189,6 +189,15 @@ def test_attention_ragged():
     _attn_case([3069], 2, scale_q=3.0, seed=32)   # long-form (C3) length
 
 
+def test_attention_many_items_per_cta():
+    """Persistent schedule: every CTA walks several work items, with odd and even numbers of query tiles mixed (single-tile
+    items idle softmax group B), tail key tiles and one-tile utterances in between."""
+    g = torch.Generator("cpu").manual_seed(5)
+    lens = [int(x) for x in torch.randint(60, 900, (48,), generator=g)] + [128, 129, 1, 257, 384]
+    _attn_case(lens, 16, seed=33)
+    _attn_case([1219] * 6 + [1100] * 5, 16, scale_q=4.0, seed=34)
+
+
 def test_layernorm_mod():
     for D in (128, 256, 512, 1024):
         M = 1001

@@ -44,7 +44,7 @@ constexpr uint32_t ATT_TM_S = 0, ATT_TM_P = 256, ATT_TM_O = 384;   // column off
 #define ATT_EXP_BF16X2 0    // 1: ex2.approx.ftz.bf16x2 (two exponentials per MUFU op); A/B switch, see tools/attn_bench.py
 #endif
 #ifndef ATT_POLY_COUNT
-#define ATT_POLY_COUNT 0      // of every ATT_POLY_PERIOD score pairs, this many take the polynomial exp2 path (FMA pipes) instead of the MUFU
+#define ATT_POLY_COUNT 1      // of every ATT_POLY_PERIOD score pairs, this many take the polynomial exp2 path (FMA pipes) instead of the MUFU
 #endif
 #ifndef ATT_EXP_PIPE
 #define ATT_EXP_PIPE 0
