@@ -1,5 +1,8 @@
+"""clock64 event trace of CTA 0 of the attention kernel.  Needs the trace build of the library:
+  F5_LIB_SUFFIX=_trace F5_NVCC_EXTRA=-DATT_TRACE=1 python -m tts_indic_server_f5_b200.build --force   (then run this under gpurun)"""
 import ctypes, os, sys
 os.environ["F5_ATTN_TRACE"] = "1"
+os.environ.setdefault("F5_LIB_SUFFIX", "_trace")
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from tts_indic_server_f5_b200 import ops, _lib
@@ -26,7 +29,7 @@ print("MMA events (per step: top, next QKs issued, PVs issued) first 45:", m[:45
 for r in (2, 3):
     s = a[r][:512].reshape(-1, 8)[:, :6]
     s = s[(s > 0).all(axis=1)] - t0
-    print(f"softmax group {r-2}: per tile [s_full seen, +S in regs, +max/grow, +o_full/readout/rescale, +exps, +st wait & p_full arrive | gap to next s_full] first 14:")
+    print(f"softmax group {r-2}: per tile [s_full seen, +S in regs, +max/grow/gate, +exp chunks 0-1 and o_full wait/read-out/rescale, +exp chunks 2-3, +st wait & p_full arrive | gap to next s_full] first 14:")
     for k, row in enumerate(s[:14]):
         nxt = int(s[k + 1][0] - row[5]) if k + 1 < len(s) else -1
         print("   ", int(row[0]), np.diff(row).tolist(), "| gap", nxt, " total", int(row[5] - row[0]))

@@ -27,7 +27,7 @@ xres = torch.randn(M, D, device=dev)
 gate = torch.randn(D, device=dev)
 tiles = L.attn_tiles.to(dev)
 W2 = (torch.randn(D, 2 * D, device=dev) / 45).to(torch.bfloat16)
-for rep in range(2):           # launch order per repetition: QKV, attention, out-proj, FF1, FF2 (one DiT layer)
+for rep in range(1):           # launch order per repetition: QKV, attention, out-proj, FF1, FF2 (one DiT layer)
     ops.gemm(A, Wqkv, mode=ops.F5_EPI_STORE_BF16, bias=bias3, out=qkv)
     ops.attention(qkv, tiles, ab, 16, 0, D, 2 * D, 0.125)
     ops.gemm(ab, Wo, mode=ops.F5_EPI_RESID_F32, bias=bias1, gate=gate, resid=xres)

@@ -87,7 +87,14 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr) {
   return d;
 }
 
+#ifndef ATT_TRACE
+#define ATT_TRACE 0           // 1: clock64 event trace of CTA 0 (tools/attn_trace.py builds this variant); costs instructions, off in the product
+#endif
+#if ATT_TRACE
 #define F5_TRACE(role, idx) do { if (p.trace != nullptr && blockIdx.x == 0 && (idx) < 512) p.trace[(role) * 512 + (idx)] = clock64(); } while (0)
+#else
+#define F5_TRACE(role, idx) do { } while (0)
+#endif
 
 // Walks the CTA's flat step sequence: work items w = blockIdx.x, +gridDim.x, ...; key tiles j = 0..nkv-1 inside each.
 struct StepWalker {
@@ -290,12 +297,15 @@ attn_d64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnParams p
     asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
     // ------------------------------------------------------------------ softmax groups
     const int g = warp >> 2;                      // 0: tile A, 1: tile B
-    const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
-    const int row = quarter * 32 + lane;
-    const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
+    const int row = static_cast<int>(pin_u32(threadIdx.x & 127u));      // = TMEM lane; warp w may access lanes 32*(w%4)..
+    const uint32_t lane_off = static_cast<uint32_t>(row & 96) << 16;
     const uint32_t tmem_S = tmem_base + ATT_TM_S + g * ATT_BN + lane_off;
     const uint32_t tmem_P = tmem_base + ATT_TM_P + g * (ATT_BN / 2) + lane_off;
     const uint32_t tmem_O = tmem_base + ATT_TM_O + g * ATT_D + lane_off;
+    // barrier addresses once, as 32-bit shared-window addresses the compiler cannot rematerialise from special registers
+    const uint32_t b_s_full = pin_u32(smem_u32(&s_full[g])), b_s_free = pin_u32(smem_u32(&s_free[g]));
+    const uint32_t b_p_full = pin_u32(smem_u32(&p_full[g])), b_o_full = pin_u32(smem_u32(&o_full[g]));
+    const uint32_t b_gate = pin_u32(smem_u32(a_gate));
     const float2 sc2 = make_float2(p.scale_log2, p.scale_log2);
     uint32_t t = 0;
     // deferred read-out of the previous item's O (runs inside the first softmax of the next item)
@@ -333,7 +343,7 @@ attn_d64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnParams p
       for (int j = 0; j < nkv; ++j, ++t) {
         const int kv_valid = min(ATT_BN, kv_len - j * ATT_BN);
         const bool full = kv_valid == ATT_BN;     // only the last tile of an utterance needs key masking
-        mbar_wait(&s_full[g], t & 1);
+        mbar_wait_a(b_s_full, t & 1);
         tc_fence_after();
         if (row == 0) F5_TRACE(2 + g, 8 * t);
         // S row (128 fp32) is read from TMEM ONCE into registers, then S_g is handed back to the MMA warp at once.
@@ -345,7 +355,7 @@ attn_d64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnParams p
         tmem_ld_wait();
         if (row == 0) F5_TRACE(2 + g, 8 * t + 1);
         tc_fence_before();
-        mbar_arrive(&s_free[g]);
+        mbar_arrive_a(b_s_free);
         if (!full) {
 #pragma unroll
           for (int i = 0; i < 128; ++i)
@@ -368,13 +378,35 @@ attn_d64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnParams p
           alpha = fast_ex2(m_run - m_new);
           m_run = m_new;
         }
-        if (g == 0) mbar_arrive(a_gate);          // group B's scores for this step may be issued now (half-tile stagger)
+        if (g == 0) mbar_arrive_a(b_gate);        // group B's scores for this step may be issued now (half-tile stagger)
         if (row == 0) F5_TRACE(2 + g, 8 * t + 2);
-        // The group's previous PV (issued at the end of the previous softmax) has normally retired by now.  It must have:
-        // it reads P_g (overwritten below) and accumulates into O_g (rescaled / read out below).  Waiting for it on EVERY
-        // tile also keeps this thread exactly one phase behind o_full (a parity wait must never fall two phases behind).
+        // p = exp2(s*scale - m), row sum, P as packed bf16 pairs -> TMEM columns [c*16, c*16+16) of P_g.
+        const float2 nm2 = make_float2(-m_run, -m_run);
+        float2 ls2 = make_float2(0.f, 0.f), ls2b = make_float2(0.f, 0.f);
+        auto exp_chunk = [&](int c, uint32_t (&pk)[16]) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float2 e = ffma2(make_float2(__uint_as_float(r[c * 32 + 2 * i]), __uint_as_float(r[c * 32 + 2 * i + 1])), sc2, nm2);
+            if ((i % ATT_POLY_PERIOD) < ATT_POLY_COUNT) {   // this pair on the FMA/ALU pipes, the others on the MUFU
+              e = exp2_poly2(e);
+            } else {
+              e.x = fast_ex2(e.x);
+              e.y = fast_ex2(e.y);
+            }
+            if (i & 1) ls2b = fadd2(ls2b, e); else ls2 = fadd2(ls2, e);
+            pk[i] = pack_bf16x2(e.x, e.y);
+          }
+        };
+        // The first two chunks are computed BEFORE waiting for the group's previous PV: that PV (issued at the end of the
+        // previous softmax, ~600 cycles of issue + tensor + commit latency) still reads P_g and accumulates into O_g, so
+        // only the tcgen05.st of P, the O rescale and the deferred read-out have to wait for it — the exponentials do not
+        // (ncu: 60 % of the tiles stalled ~300 cycles here when the wait came first).  Waiting on EVERY tile also keeps
+        // this thread exactly one phase behind o_full (a parity wait must never fall two phases behind).
+        uint32_t pk0[16], pk1[16];
+        exp_chunk(0, pk0);
+        exp_chunk(1, pk1);
         if (t > 0) {
-          mbar_wait(&o_full[g], (t - 1) & 1);
+          mbar_wait_a(b_o_full, (t - 1) & 1);
           tc_fence_after();
         }
         if (pend) read_out();                     // previous item's O / l -> bf16 output rows, before PV(this item, 0) overwrites O_g
@@ -390,78 +422,19 @@ attn_d64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnParams p
           }
         }
         if (row == 0) F5_TRACE(2 + g, 8 * t + 3);
-        // p = exp2(s*scale - m), row sum, P as packed bf16 pairs -> TMEM columns [c*16, c*16+16) of P_g
-        const float2 nm2 = make_float2(-m_run, -m_run);
-        float2 ls2 = make_float2(0.f, 0.f);
-#if ATT_EXP_PIPE
-        // Software pipeline over 32-key chunks: the exponentials of chunk c are issued before the sums / bf16 packing /
-        // TMEM store of chunk c-1, so no consumer sits within the MUFU's latency of its producer (one warp per
-        // sub-partition is in this phase at a time — there is no second warp to hide that latency).
-        float2 ls2b = make_float2(0.f, 0.f);
-        auto exps = [&](int c) {
+        tmem_st_32x32b_x16(tmem_P, pk0);
+        tmem_st_32x32b_x16(tmem_P + 16, pk1);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            float2 e = ffma2(make_float2(__uint_as_float(r[c * 32 + 2 * i]), __uint_as_float(r[c * 32 + 2 * i + 1])), sc2, nm2);
-            if ((i % ATT_POLY_PERIOD) < ATT_POLY_COUNT) {
-              e = exp2_poly2(e);
-            } else {
-              e.x = fast_ex2(e.x);
-              e.y = fast_ex2(e.y);
-            }
-            r[c * 32 + 2 * i] = __float_as_uint(e.x);
-            r[c * 32 + 2 * i + 1] = __float_as_uint(e.y);
-          }
-        };
-        auto consume = [&](int c) {
+        for (int c = 2; c < ATT_BN / 32; ++c) {
           uint32_t pk[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float2 e = make_float2(__uint_as_float(r[c * 32 + 2 * i]), __uint_as_float(r[c * 32 + 2 * i + 1]));
-            if (i & 1) ls2b = fadd2(ls2b, e); else ls2 = fadd2(ls2, e);
-            pk[i] = pack_bf16x2(e.x, e.y);
-          }
-          tmem_st_32x32b_x16(tmem_P + c * 16, pk);
-        };
-        exps(0);
-#pragma unroll
-        for (int c = 1; c < ATT_BN / 32; ++c) {
-          exps(c);
-          consume(c - 1);
-        }
-        consume(ATT_BN / 32 - 1);
-        ls2 = fadd2(ls2, ls2b);
-#else
-#pragma unroll
-        for (int c = 0; c < ATT_BN / 32; ++c) {
-          uint32_t pk[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            float2 e = ffma2(make_float2(__uint_as_float(r[c * 32 + 2 * i]), __uint_as_float(r[c * 32 + 2 * i + 1])), sc2, nm2);
-#if ATT_EXP_BF16X2
-            // one MUFU op yields both exponentials, already in the bf16 the PV MMA consumes; the row sum is taken over the
-            // SAME rounded values (numerator and denominator stay consistent).
-            const uint32_t pb = ex2_bf16x2(pack_bf16x2(e.x, e.y));
-            pk[i] = pb;
-            ls2 = fadd2(ls2, make_float2(__uint_as_float(pb << 16), __uint_as_float(pb & 0xffff0000u)));
-#else
-            if ((i % ATT_POLY_PERIOD) < ATT_POLY_COUNT) {   // this pair on the FMA/ALU pipes, the others on the MUFU
-              e = exp2_poly2(e);
-            } else {
-              e.x = fast_ex2(e.x);
-              e.y = fast_ex2(e.y);
-            }
-            ls2 = fadd2(ls2, e);
-            pk[i] = pack_bf16x2(e.x, e.y);
-#endif
-          }
+          exp_chunk(c, pk);
           tmem_st_32x32b_x16(tmem_P + c * 16, pk);
         }
-#endif
-        l_run = l_run * alpha + (ls2.x + ls2.y);
+        l_run = l_run * alpha + ((ls2.x + ls2b.x) + (ls2.y + ls2b.y));
         if (row == 0) F5_TRACE(2 + g, 8 * t + 4);
         tmem_st_wait();
         tc_fence_before();
-        mbar_arrive(&p_full[g]);
+        mbar_arrive_a(b_p_full);
         if (row == 0) F5_TRACE(2 + g, 8 * t + 5);
       }
       pend = true;
@@ -469,7 +442,7 @@ attn_d64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnParams p
       pend_out = row < q_valid ? p.out + static_cast<size_t>(it.x + g * ATT_BM + row) * p.ldo + head * ATT_D : nullptr;
     }
     if (pend) {
-      mbar_wait(&o_full[g], (t - 1) & 1);
+      mbar_wait_a(b_o_full, (t - 1) & 1);
       tc_fence_after();
       read_out();
     }

@@ -55,21 +55,63 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 // try_wait suspends the thread in hardware for a bounded time, so the loop is not a hot spin; the watchdog clock is only
-// read every 4096 polls to keep the polling warps (one lane each) off the issue slots the math warps need.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
+// read every 4096 polls to keep the polling warps (one lane each) off the issue slots the math warps need.  A stuck
+// pipeline traps instead of hanging the GPU; build with -DF5_WATCHDOG_PRINT=1 to also print which barrier it was (the
+// printf call inlined at every wait bloats the attention kernel past the instruction cache and costs registers, and an
+// out-of-line slow path makes ptxas spill the softmax's 128-register score row around the call).
+#ifndef F5_WATCHDOG_PRINT
+#define F5_WATCHDOG_PRINT 0
+#endif
+__device__ __forceinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
   long long t0 = 0;
   for (uint32_t polls = 1;; ++polls) {
-    if (mbar_try_wait(bar, parity)) return;
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) return;
     if ((polls & 4095u) == 0) {
       const long long now = clock64();
       if (t0 == 0) t0 = now;
       if (now - t0 > F5_WATCHDOG_CYCLES) {
-        printf("f5: mbarrier watchdog: block %d thread %d bar %u parity %u\n", blockIdx.x, threadIdx.x, smem_u32(bar), parity);
+#if F5_WATCHDOG_PRINT
+        printf("f5: mbarrier watchdog: block %d thread %d bar %u parity %u\n", blockIdx.x, threadIdx.x, bar, parity);
+#endif
         __trap();
       }
     }
   }
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  mbar_wait_slow(smem_u32(bar), parity);
+}
+// Variants on a 32-bit shared-window address computed ONCE by the caller (the generic-pointer forms re-derive the window
+// base from special registers at every call: S2R + LEA on the critical path of each barrier operation).
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  if (ok) return;
+  mbar_wait_slow(bar, parity);
+}
+__device__ __forceinline__ void mbar_arrive_a(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// value the compiler may not rematerialise (keeps special-register reads / address arithmetic out of inner loops)
+__device__ __forceinline__ uint32_t pin_u32(uint32_t v) {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(v));
+  return r;
 }
 
 // generic-proxy writes to smem -> visible to the async proxy (UMMA / TMA store)
