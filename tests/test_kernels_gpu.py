@@ -84,6 +84,24 @@ def test_gemm_resid_gate():
     check("gemm_resid_mish_nogate", x, x0 + F.mish(A.float() @ B.float().t() + bias), rel=2e-5, amax=3e-4)
 
 
+@pytest.mark.parametrize("M,N,K,act,use_gate", [(130, 512, 1536, 0, True), (777, 1024, 2048, 0, True), (1000, 96, 128, 2, False),
+                                               (4096, 1024, 1024, 0, True), (257, 512, 320, 1, False)])
+def test_gemm_resid_shapes(M, N, K, act, use_gate):
+    """Residual epilogue through the TMA reduce-add (N % 32 == 0): ragged M (rows clipped by the tensor map, whole 32-row boxes
+    out of range), narrow N (units beyond N skipped), activations, missing gate."""
+    A = rnd(M, K, seed=13, dtype=torch.bfloat16)
+    B = rnd(N, K, seed=14, scale=1 / math.sqrt(K), dtype=torch.bfloat16)
+    bias, gate, x0 = rnd(N, seed=15), rnd(N, seed=16), rnd(M + 64, N, seed=17)
+    x = x0.clone()
+    ops.gemm(A, B, mode=ops.F5_EPI_RESID_F32, act=act, bias=bias, gate=gate if use_gate else None, resid=x[:M])
+    torch.cuda.synchronize()
+    z = A.float() @ B.float().t() + bias
+    z = [z, F.gelu(z, approximate="tanh"), F.gelu(z), F.mish(z)][act]
+    want = x0[:M] + (gate if use_gate else 1.0) * z
+    check(f"gemm_resid {M}x{N}x{K} act{act}", x[:M], want, rel=2e-5, amax=4e-4)
+    assert torch.equal(x[M:], x0[M:]), "rows beyond M were touched"
+
+
 def test_gemm_qkv_rope():
     D, M = 256, 400
     A = rnd(M, D, seed=13, dtype=torch.bfloat16)

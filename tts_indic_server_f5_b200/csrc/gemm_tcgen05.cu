@@ -26,9 +26,9 @@ struct GemmCfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = BLOCK_N == 256 ? 4 : (BLOCK_N == 128 ? 6 : 8);
   static constexpr int TMEM_COLS = 2 * BLOCK_N;  // 512 / 256 / 128: powers of two >= 32
-  static constexpr int EPI_STAGE_BYTES = 4 * 4096;   // one 32-row x 128-B staging tile per epilogue warp
-  static constexpr int EPI_BIAS_BYTES = 4 * BLOCK_N * 4;   // per-warp copy of the tile's bias slice
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGE_BYTES + EPI_BIAS_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int EPI_STAGE_BYTES = 4 * 2 * 4096;   // two 32-row x 128-B staging tiles per epilogue warp (double buffer of the TMA reduce path)
+  static constexpr int EPI_BIAS_BYTES = 2 * BLOCK_N * 4;  // the tile's bias and gate slices, shared by the four epilogue warps
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGE_BYTES + EPI_BIAS_BYTES + 256 /*barriers*/;
 };
 
 struct GemmParams {
@@ -43,6 +43,7 @@ struct GemmParams {
   float* resid; long long ldr;
   const int* row_pos; int mask_rows;
   const float* rope; int rope_period, rope_tiles;
+  int resid_tma;   // RESID mode through TMA reduce-add (N % 32 == 0)
 };
 
 // The activation is a compile-time parameter: a runtime switch would inline all three bodies into every unrolled
@@ -55,13 +56,16 @@ __device__ __forceinline__ float apply_act(float v) {
   else return v;
 }
 
+// named barrier 1: the four epilogue warps (128 threads)
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
 template <int BLOCK_N, int ACT>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                    const GemmParams p) {
+                    const __grid_constant__ CUtensorMap tmap_r, const GemmParams p) {
   using Cfg = GemmCfg<BLOCK_N>;
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();   // 128B-swizzled tiles need 1024-B aligned bases (no static smem in this kernel)
   uint8_t* stage_base = smem + Cfg::STAGES * Cfg::STAGE_BYTES;
   float* bias_base = reinterpret_cast<float*>(stage_base + Cfg::EPI_STAGE_BYTES);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(stage_base + Cfg::EPI_STAGE_BYTES + Cfg::EPI_BIAS_BYTES);
@@ -77,6 +81,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
+    if (p.resid_tma) tma_prefetch_desc(&tmap_r);
     for (int i = 0; i < Cfg::STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
@@ -155,7 +160,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     // float4 per unit.  All side loads are issued a unit ahead: with ~210 KB of smem carved out the L1 is tiny, so a
     // dependent global load on the critical path costs an L2 round trip.
     const int quarter = warp & 3;           // TMEM lane quarter this warp may access
-    uint8_t* stg = stage_base + (warp - 2) * 4096;
+    uint8_t* stg = stage_base + (warp - 2) * 8192;
     const int rd_row = lane >> 3, rd_chunk = lane & 7;
     constexpr int UNITS = BLOCK_N / 32;
     const float* side = p.mode == F5_EPI_RESID_F32 ? p.resid : (p.mode == F5_EPI_STORE_F32 ? p.addend : nullptr);
@@ -192,9 +197,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       if (p.mode == F5_EPI_STORE_BF16) {
         // bf16 outputs: 64-column units (one full 128-B line per row), math in the thread = row layout, the tile's bias slice
         // served from a per-warp smem copy (fetched before the accumulator wait).
-        float* bias_s = bias_base + (warp - 2) * BLOCK_N;
-#pragma unroll
-        for (int c = lane * 4; c < BLOCK_N; c += 128) {
+        float* bias_s = bias_base;
+        epi_bar_sync();                                    // every epilogue warp is done with the previous tile's slice
+        for (int c = (threadIdx.x - 64) * 4; c < BLOCK_N; c += 512) {
           const float4 b = (p.bias != nullptr && n0 + c < p.N) ? *reinterpret_cast<const float4*>(p.bias + n0 + c)
                                                                : make_float4(0.f, 0.f, 0.f, 0.f);
           *reinterpret_cast<float4*>(bias_s + c) = b;
@@ -202,7 +207,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         const int m = mw + lane;
         const int pos = (p.row_pos != nullptr && m < p.M) ? p.row_pos[m] : 0;
         const bool zero_row = p.mask_rows && pos < 0;
-        __syncwarp();
+        epi_bar_sync();
         mbar_wait(&tmem_full[acc], acc_phase);
         tc_fence_after();
 #pragma unroll 1
@@ -265,6 +270,60 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         continue;
       }
+      if (p.resid_tma) {
+        // x += gate * act(acc + bias) WITHOUT reading x into the SM: the update tile goes to smem (thread = row, 128-B rows,
+        // 16-B chunks XOR-swizzled by row = the layout of a SWIZZLE_128B box) and one lane hands it to the TMA as a
+        // reduce-add (`cp.reduce.async.bulk.tensor ... .add.f32`); the read-modify-write happens at the L2.  The previous
+        // form loaded the residual tile through registers one 32-column unit ahead: 16 KB in flight per SM against the
+        // ~45 KB the HBM latency-bandwidth product needs, so the K = 1024 out-projection ran at half of either roofline.
+        float* bias_s = bias_base;
+        float* gate_s = bias_base + BLOCK_N;
+        epi_bar_sync();
+        for (int c = (threadIdx.x - 64) * 4; c < BLOCK_N; c += 512) {
+          const bool cok = n0 + c < p.N;
+          *reinterpret_cast<float4*>(bias_s + c) = (p.bias != nullptr && cok) ? *reinterpret_cast<const float4*>(p.bias + n0 + c)
+                                                                               : make_float4(0.f, 0.f, 0.f, 0.f);
+          *reinterpret_cast<float4*>(gate_s + c) = (p.gate != nullptr && cok) ? *reinterpret_cast<const float4*>(p.gate + n0 + c)
+                                                                               : make_float4(1.f, 1.f, 1.f, 1.f);
+        }
+        epi_bar_sync();
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tc_fence_after();
+#pragma unroll 1
+        for (int u = 0; u < UNITS; ++u) {
+          uint32_t r0[32];
+          tmem_ld_32x32b_x32(taddr + u * 32, r0);
+          tmem_ld_wait();
+          if (u + 1 == UNITS) {                            // accumulator fully read: the MMA warp may start tile i+2 in it
+            tc_fence_before();
+            mbar_arrive(&tmem_empty[acc]);
+          }
+          uint8_t* buf = stg + (u & 1) * 4096;
+          if (lane == 0) bulk_wait_group_read<1>();        // the reduce that last read this buffer (two units ago) is done with it
+          __syncwarp();
+          if (n0 + u * 32 < p.N) {                         // warp-uniform
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float4 b = *reinterpret_cast<const float4*>(bias_s + u * 32 + 4 * q);
+              const float4 g = *reinterpret_cast<const float4*>(gate_s + u * 32 + 4 * q);
+              float4 y = make_float4(__uint_as_float(r0[4 * q]) + b.x, __uint_as_float(r0[4 * q + 1]) + b.y,
+                                     __uint_as_float(r0[4 * q + 2]) + b.z, __uint_as_float(r0[4 * q + 3]) + b.w);
+              if constexpr (ACT != F5_ACT_NONE) {
+                y.x = apply_act<ACT>(y.x); y.y = apply_act<ACT>(y.y); y.z = apply_act<ACT>(y.z); y.w = apply_act<ACT>(y.w);
+              }
+              *reinterpret_cast<float4*>(buf + lane * 128 + ((q ^ (lane & 7)) << 4)) = make_float4(g.x * y.x, g.y * y.y, g.z * y.z, g.w * y.w);
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_reduce_add_2d(&tmap_r, buf, n0 + u * 32, mw);   // rows >= M / cols >= N are clipped by the tensor map
+              bulk_commit_group();
+            }
+          }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        continue;
+      }
       prefetch(0);                           // in flight while we wait for the accumulator
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
@@ -315,6 +374,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       mbar_arrive(&tmem_empty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (p.resid_tma && lane == 0) bulk_wait_group<0>();   // every reduce-add of this warp has completed
   }
 
   tc_fence_before();
@@ -360,14 +420,35 @@ int make_tmap_bf16_2d(CUtensorMap* map, const void* base, long long rows, long l
   return r == CUDA_SUCCESS ? F5_OK : F5_ERR_DRIVER;
 }
 
+// 2-D fp32 tensor [rows, cols] with row stride ld (elements); box = {32 cols, 32 rows} = 32 rows of 128 B; 128-B swizzle.
+int make_tmap_f32_2d_box32(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld) {
+  EncodeTiledFn enc = get_encode_tiled();
+  if (enc == nullptr) return F5_ERR_DRIVER;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld % 4) != 0 || rows <= 0 || cols <= 0) return F5_ERR_ARG;
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * 4};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? F5_OK : F5_ERR_DRIVER;
+}
+
 template <int BLOCK_N, int ACT>
 int launch_gemm(const f5_gemm_args& a, const GemmParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg<BLOCK_N>;
-  CUtensorMap ta, tb;
+  CUtensorMap ta, tb, tr;
   int rc = make_tmap_bf16_2d(&ta, a.A, a.a_rows, a.a_cols, a.lda, BLOCK_M);
   if (rc != F5_OK) return rc;
   rc = make_tmap_bf16_2d(&tb, a.B, a.b_rows, a.b_cols, a.ldb, BLOCK_N);
   if (rc != F5_OK) return rc;
+  if (p.resid_tma) {
+    rc = make_tmap_f32_2d_box32(&tr, a.resid, a.M, a.N, a.ldr);
+    if (rc != F5_OK) return rc;
+  } else {
+    tr = ta;
+  }
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BLOCK_N, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -378,7 +459,7 @@ int launch_gemm(const f5_gemm_args& a, const GemmParams& p, cudaStream_t stream)
   const int sms = a.num_sms > 0 ? a.num_sms : kNumSMsB200;
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   const int grid = tiles < sms ? tiles : sms;
-  gemm_tcgen05_kernel<BLOCK_N, ACT><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, p);
+  gemm_tcgen05_kernel<BLOCK_N, ACT><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, tr, p);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -404,6 +485,7 @@ extern "C" int f5_gemm_bf16(const f5_gemm_args* a, void* stream) {
   p.resid = a->resid; p.ldr = a->ldr;
   p.row_pos = a->row_pos; p.mask_rows = a->mask_rows;
   p.rope = a->rope; p.rope_period = a->rope_period > 0 ? a->rope_period : 1; p.rope_tiles = a->rope_tiles;
+  p.resid_tma = (a->mode == F5_EPI_RESID_F32 && (a->N % 32) == 0) ? 1 : 0;
   switch (a->mode) {
     case F5_EPI_STORE_BF16:
       if (a->out == nullptr || (a->ldo % 8) != 0) return F5_ERR_ARG;
