@@ -137,6 +137,14 @@ int f5_istft_frames(const float* spec, int64_t lds, int32_t rows, const float* w
 int f5_istft_ola(const float* frames, const float* window, const int32_t* seg, int32_t num_segs, int32_t max_wav_len,
                  float* wav, const float* gains, void* stream);
 
+/* Prompt log-mel front-end (model/modules.py:75-101 `get_vocos_mel_spectrogram`; torchaudio MelSpectrogram n_fft 1024, hop 256,
+ * periodic hann, center=True with reflect padding, power 1, HTK mel scale, norm None; then log(clamp(1e-5))).
+ * wave: fp32 samples of all prompts back to back; seg: int32 [num_segs, 4] = {first sample, samples, first output row,
+ * frames (= 1 + samples / 256)}; window: fp32 [1024]; fbank: fp32 [513, n_mels]; band: int32 [n_mels, 2] = the half-open
+ * range of frequency bins where column m of fbank is non-zero; mel: fp32 [rows, ldm], one row per frame. */
+int f5_mel_frames(const float* wave, const int32_t* seg, int32_t num_segs, int32_t max_frames, const float* window,
+                  const float* fbank, const int32_t* band, int32_t n_mels, float* mel, int64_t ldm, void* stream);
+
 /* Library / device info. */
 int f5_device_check(void);      /* 0 if the current device is sm_100 */
 const char* f5_version(void);

@@ -6,6 +6,7 @@ import subprocess
 import tempfile
 
 import pytest
+import numpy as np
 import torch
 import torch.nn.functional as F
 
@@ -73,6 +74,33 @@ def test_lpt_partition_balances_and_covers():
         assert sorted(i for p in parts for i in p) == list(range(512))
         loads = [sum(utterance_cost(lens[i]) for i in p) for p in parts]
         assert max(loads) / (sum(loads) / w) < 1.02          # <2 % imbalance at 64 utterances / GPU
+
+
+def test_scheduler_packing_and_cross_fade():
+    """Request scheduler host logic: packs cover every utterance once, respect the row and count
+    budgets, are length-bucketed; the cross-fade equals the reference's formula (utils_infer.py:485-519)."""
+    from tts_indic_server_f5_b200.layout import build_layout
+    from tts_indic_server_f5_b200.scheduler import cross_fade, pack_rows, plan_packs
+    g = torch.Generator().manual_seed(3)
+    lengths = [int(x) for x in torch.randint(300, 4097, (200,), generator=g)]
+    packs = plan_packs(lengths, max_rows=65536, max_utts=24)
+    assert sorted(i for p in packs for i in p) == list(range(200))
+    for p in packs:
+        assert len(p) <= 24
+        rows = pack_rows([lengths[i] for i in p])
+        assert rows == build_layout([lengths[i] for i in p]).rows          # the planner's row count is the engine's
+        assert rows <= 65536 or len(p) == 1
+    firsts = [lengths[p[0]] for p in packs]
+    assert firsts == sorted(firsts, reverse=True)                          # longest-first buckets
+    assert plan_packs([5000], max_rows=1024) == [[0]]                      # an oversize utterance still runs, alone
+    assert plan_packs([], 1024) == []
+    a, b, c = (np.random.RandomState(k).randn(n).astype(np.float32) for k, n in ((0, 9000), (1, 5000), (2, 100)))
+    n = int(0.15 * 24000)
+    want = np.concatenate([a[:-n], a[-n:] * np.linspace(1, 0, n) + b[:n] * np.linspace(0, 1, n), b[n:]])
+    np.testing.assert_array_equal(cross_fade([a, b]), want)
+    got = cross_fade([a, b, c])                                            # third chunk shorter than the fade window
+    assert len(got) == len(want) + len(c) - min(n, len(c))
+    np.testing.assert_array_equal(cross_fade([a, b], 0.0), np.concatenate([a, b]))
 
 
 def test_conv_pos_weight_block_diagonal_is_exact():

@@ -55,10 +55,33 @@ def test_oracle_prompt_mel_matches_golden(golden_dir):
     np.testing.assert_allclose(m, g["prompt_mel"], rtol=0, atol=1e-5)
 
 
-def test_product_mel_frontend_matches_oracle():
-    from tts_indic_server_f5_b200.melspec import mel_spectrogram
-    w = S.prompt_audio(1.0, 3)
-    np.testing.assert_allclose(mel_spectrogram(w).numpy(), O.mel_spectrogram(w).numpy(), rtol=0, atol=1e-5)
+def test_product_mel_tables_and_prompt_cache():
+    """Host side of the prompt front-end (the arithmetic is the f5_mel_frames CUDA kernel, tested with -m gpu): the HTK
+    filterbank equals torchaudio's (the reference's MelSpectrogram, modules.py:83-93), the non-zero bin ranges cover
+    every non-zero weight, the cache is LRU and keyed by the samples, and there is no CPU path."""
+    from tts_indic_server_f5_b200 import melspec as M
+    fb = M.htk_fbank(513, 100, 24000)
+    try:
+        import torchaudio
+        ref = torchaudio.functional.melscale_fbanks(513, 0.0, 12000.0, 100, 24000, norm=None, mel_scale="htk")
+        assert torch.equal(fb, ref)
+    except ImportError:
+        pass
+    assert torch.equal(fb, O.mel_filterbank_htk(513, 100, 24000))
+    band = M.band_ranges(fb)
+    for m in range(100):
+        k0, k1 = int(band[m, 0]), int(band[m, 1])
+        assert k1 > k0 and float(fb[:k0, m].abs().sum()) == 0.0 and float(fb[k1:, m].abs().sum()) == 0.0
+    c = M.PromptCache(capacity=2)
+    a, b, d = S.prompt_audio(0.3, 1), S.prompt_audio(0.3, 2), S.prompt_audio(0.3, 3)
+    ka, kb, kd = M.PromptCache.key(a), M.PromptCache.key(b), M.PromptCache.key(d)
+    assert ka != kb and ka == M.PromptCache.key(a.clone())
+    c.put(ka, "cuda:0", "A"); c.put(kb, "cuda:0", "B")
+    assert c.get(ka, "cuda:0") == "A" and c.get(ka, "cuda:1") is None
+    c.put(kd, "cuda:0", "D")                       # evicts B (least recently used)
+    assert c.get(kb, "cuda:0") is None and c.get(ka, "cuda:0") == "A" and c.get(kd, "cuda:0") == "D"
+    with pytest.raises(RuntimeError):
+        M.mel_spectrogram(a)                       # CPU tensor: the product path has no CPU fallback
 
 
 @pytest.mark.skipif(not R.reference_available(), reason="reference tree only exists in the build container")

@@ -138,6 +138,58 @@ def test_vocos_decode_vs_oracle(tiny_models):
         assert snr(got, ref) > WAVE_SNR, (B, T_, snr(got, ref))
 
 
+def test_prompt_mel_kernel_vs_oracle_and_golden(golden_dir):
+    """f5_mel_frames (reflect pad, hann, 1024-pt FFT, HTK mel, log) against the oracle's torch.stft restatement of the
+    reference's get_vocos_mel_spectrogram and against the prompt mel the REAL reference produced (tests/golden/tiny.npz);
+    ragged batch in one launch; edge lengths (multiple of the hop, shorter than one frame + reflect both sides)."""
+    from tts_indic_server_f5_b200 import melspec as M
+    g = np.load(os.path.join(golden_dir, "tiny.npz"))
+    w0 = S.prompt_audio(0.6, 0)
+    got = M.mel_spectrogram(w0.cuda())[0].cpu().numpy()
+    np.testing.assert_allclose(got, g["prompt_mel"], rtol=0, atol=2e-4)      # log-mel range is ~[-11.5, 3]
+    waves = [S.prompt_audio(5.0, 1)[0], S.prompt_audio(1.0, 2)[0], S.prompt_audio(0.3, 3)[0][:7000], S.prompt_audio(0.2, 4)[0][:768]]
+    rows = M.mel_rows([w.cuda() for w in waves])
+    for w, r in zip(waves, rows):
+        want = O.mel_spectrogram(w[None])[0].t().numpy()
+        assert r.shape == want.shape == (1 + w.numel() // 256, 100)
+        err = np.abs(r.cpu().numpy() - want)
+        # bins at the 1e-5 clamp amplify fp32 FFT round-off; everything audible agrees to 1e-4
+        assert err.max() < 5e-3 and np.median(err) < 2e-5, (err.max(), np.median(err))
+    lin = np.exp(rows[0].cpu().numpy()) - np.exp(O.mel_spectrogram(waves[0][None])[0].t().numpy())
+    assert np.abs(lin).max() < 1e-4 * np.exp(rows[0].cpu().numpy()).max()
+
+
+def test_prompt_cache_reuses_the_voice(tiny_models):
+    cfg, vcfg, sd, vsd, model, voc = tiny_models
+    syn = api.Synthesizer(model, voc)
+    specs = S.workload("tiny3")
+    a = syn.generate(specs)
+    first = (syn.prompt_cache.hits, syn.prompt_cache.misses)
+    b = syn.generate(specs)
+    assert syn.prompt_cache.hits > first[0] and syn.prompt_cache.misses == first[1]
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)                # cached mel == recomputed mel, bit for bit
+
+
+def test_request_scheduler_equals_per_request_calls(tiny_models, tmp_path):
+    """Two concurrent requests (one multi-chunk) through RequestScheduler == `infer_process` per request, bit for bit:
+    chunks of different requests share packs, the noise index and the cross-fade stay per request."""
+    cfg, vcfg, sd, vsd, model, voc = tiny_models
+    audio = S.prompt_audio(5.0, 7)                                            # 5 s prompt: max_chars = ref_bytes / 5 * 20
+    ref_text = T.finish_ref_text(T.synthetic_indic_text(30, 1, "kannada"))
+    texts = [T.synthetic_indic_text(60, 2, "kannada"), " ".join(T.synthetic_indic_text(40, 10 + k, "devanagari") + "." for k in range(4))]
+    sched = api.RequestScheduler(api.Synthesizer(model, voc), max_rows=6144, max_utts=3, nfe_step=8)
+    ids = [sched.submit((audio, 24000), ref_text, t) for t in texts]
+    assert len(sched.pending[1].chunks) >= 2                                 # the second text does not fit one chunk
+    out = sched.run()
+    assert sched.pending == [] and len(sched.last_packs) >= 2                # the row budget forced several packs
+    for rid, t in zip(ids, texts):
+        wave, sr, mel = api.infer_process((audio, 24000), ref_text, t, model, voc, nfe_step=8)
+        assert sr == out[rid][1] == 24000
+        np.testing.assert_array_equal(out[rid][0], wave)
+        np.testing.assert_array_equal(out[rid][2], mel)
+
+
 def test_istft_perfect_reconstruction_property():
     """Size-independent property of the ISTFT kernels: analysing a signal with the matching STFT and feeding
     (log|X|, angle X) back reconstructs the signal (hann, hop = n_fft/4 satisfies COLA)."""

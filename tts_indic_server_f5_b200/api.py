@@ -21,7 +21,8 @@ import torch
 
 from . import text as T
 from .engine import F5Engine, UtteranceInput
-from .melspec import mel_spectrogram
+from .melspec import PromptCache, mel_rows, mel_spectrogram
+from .scheduler import RequestScheduler, cross_fade  # noqa: F401
 from .synthetic import UtteranceSpec
 from .vocos import VocosEngine
 from .weights import (INDICF5, VOCOS_24K, DiTConfig, VocosConfig, infer_dit_config, make_dit_state_dict,
@@ -268,6 +269,7 @@ class Synthesizer:
         self.device = model_obj.device
         self.last_h2d_bytes = 0
         self.last_d2h_bytes = 0
+        self.prompt_cache = PromptCache()
 
     def _prep(self, spec: UtteranceSpec, speed_, fix_duration_) -> _Prepared:
         audio = spec.audio
@@ -300,16 +302,29 @@ class Synthesizer:
         model, dev = self.model, self.device
         preps = [self._prep(s, speed, fix_duration) for s in specs]
         mels: list = [None] * len(preps)
-        by_len: dict[int, list[int]] = {}
-        for i, p in enumerate(preps):
-            by_len.setdefault(p.audio.shape[-1], []).append(i)
         h2d = 0
-        for nw, idx in by_len.items():                                            # same-length prompts share one STFT
-            host = torch.stack([preps[i].audio[0] for i in idx]).pin_memory()
+        todo: dict[bytes, list[int]] = {}
+        for i, p in enumerate(preps):                                             # one mel per distinct prompt (voice cache)
+            k = PromptCache.key(p.audio)
+            m = self.prompt_cache.get(k, dev)
+            if m is not None:
+                mels[i] = m
+            else:
+                todo.setdefault(k, []).append(i)
+        if todo:
+            firsts = [idx[0] for idx in todo.values()]
+            host = torch.cat([preps[i].audio[0] for i in firsts]).pin_memory()    # all new prompts: one H2D copy, one launch
             h2d += host.numel() * 4
-            m = mel_spectrogram(host.to(dev, non_blocking=True)).permute(0, 2, 1)
-            for j, i in enumerate(idx):
-                mels[i] = m[j]
+            flat = host.to(dev, non_blocking=True)
+            waves_d, o = [], 0
+            for i in firsts:
+                n = preps[i].audio.shape[-1]
+                waves_d.append(flat[o:o + n])
+                o += n
+            for (k, idx), m in zip(todo.items(), mel_rows(waves_d)):
+                self.prompt_cache.put(k, dev, m)
+                for i in idx:
+                    mels[i] = m
         ids = T.list_str_to_idx([p.tokens for p in preps], model.vocab_char_map)
         noise = y0 if y0 is not None else [initial_noise(4096, p.noise_index) for p in preps]
         utts = []
@@ -378,17 +393,7 @@ def infer_batch_process(ref_audio, ref_text, gen_text_batches, model_obj, vocode
              for i, g in enumerate(gen_text_batches)]
     waves, mels = Synthesizer(model_obj, vocoder).generate(specs, nfe_step, cfg_strength, sway_sampling_coef, speed,
                                                            fix_duration, y0=y0, return_mel=True)
-    if cross_fade_duration <= 0:
-        final_wave = np.concatenate(waves)
-    else:                                                                         # :485-519
-        final_wave = waves[0]
-        for nxt in waves[1:]:
-            n = min(int(cross_fade_duration * target_sample_rate), len(final_wave), len(nxt))
-            if n <= 0:
-                final_wave = np.concatenate([final_wave, nxt])
-                continue
-            mixed = final_wave[-n:] * np.linspace(1, 0, n) + nxt[:n] * np.linspace(0, 1, n)
-            final_wave = np.concatenate([final_wave[:-n], mixed, nxt[n:]])
+    final_wave = cross_fade(waves, cross_fade_duration, target_sample_rate)                   # :485-519
     return final_wave, target_sample_rate, np.concatenate(mels, axis=1)
 
 

@@ -136,3 +136,12 @@ def istft(spec, window, frames, seg, max_wav_len: int, wav, gains=None) -> None:
     assert spec.dtype == F32 and frames.dtype == F32 and seg.dtype == I32 and wav.dtype == F32 and window.dtype == F32
     call("f5_istft_frames", ptr(spec), _ld(spec), spec.shape[0], ptr(window), ptr(frames), stream_ptr())
     call("f5_istft_ola", ptr(frames), ptr(window), ptr(seg), seg.shape[0], max_wav_len, ptr(wav), ptr(gains), stream_ptr())
+
+
+def mel_frames(wave: torch.Tensor, seg: torch.Tensor, max_frames: int, window: torch.Tensor, fbank: torch.Tensor,
+               band: torch.Tensor, mel: torch.Tensor) -> None:
+    """Prompt log-mel rows (f5_mel_frames): wave fp32 [samples], seg int32 [S,4], mel fp32 [rows, >= n_mels]."""
+    assert wave.dtype == F32 and mel.dtype == F32 and seg.dtype == I32 and band.dtype == I32 and fbank.dtype == F32
+    assert wave.is_contiguous() and seg.is_contiguous() and fbank.is_contiguous() and band.is_contiguous()
+    call("f5_mel_frames", ptr(wave), ptr(seg), seg.shape[0], max_frames, ptr(window), ptr(fbank), ptr(band), fbank.shape[1],
+         ptr(mel), _ld(mel), stream_ptr())
