@@ -49,61 +49,81 @@ __global__ void __launch_bounds__(256) layernorm_mod_kernel(const float* __restr
 }
 
 // ------------------------------------------------------------------------------------------------ dwconv(k=7) + LN -> bf16
+// One warp per row; a CTA (8 warps) walks blocks of 64 consecutive rows, 8 per warp, so the 6 halo rows of a row are the
+// rows its neighbour warps read (L1 hits: HBM sees every row once).  The per-channel taps, conv bias and LN affine are
+// staged ONCE per CTA in shared memory, transposed to [tap][channel] so that a lane's four channels are one LDS.128 (the
+// first version fetched 7 x 4 scalar weights per float4 of x from global memory on every row: 15 % of HBM bandwidth).
+constexpr int DW_ROWS_PER_CTA = 64;
 template <int NV>  // C = NV * 128
 __global__ void __launch_bounds__(256) dwconv7_ln_kernel(const float* __restrict__ x, long long ldx,
                                                          __nv_bfloat16* __restrict__ y, long long ldy, int M,
                                                          const int* __restrict__ row_pos, const float* __restrict__ w,
                                                          const float* __restrict__ bias, const float* __restrict__ ln_w,
                                                          const float* __restrict__ ln_b, float eps) {
-  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (row >= M) return;
-  const int lane = threadIdx.x & 31;
   constexpr int C = NV * 128;
-  uint2* yr = reinterpret_cast<uint2*>(y + static_cast<size_t>(row) * ldy);
-  const int pos = row_pos[row];
-  if (pos < 0) {
+  __shared__ float4 wT[7][NV * 32];
+  __shared__ float4 cb[NV * 32], lw[NV * 32], lb[NV * 32];
+  for (int c4 = threadIdx.x; c4 < NV * 32; c4 += blockDim.x) {
 #pragma unroll
-    for (int i = 0; i < NV; ++i) yr[i * 32 + lane] = make_uint2(0, 0);
-    return;
+    for (int k = 0; k < 7; ++k)
+      wT[k][c4] = make_float4(w[(4 * c4 + 0) * 7 + k], w[(4 * c4 + 1) * 7 + k], w[(4 * c4 + 2) * 7 + k], w[(4 * c4 + 3) * 7 + k]);
+    cb[c4] = reinterpret_cast<const float4*>(bias)[c4];
+    lw[c4] = reinterpret_cast<const float4*>(ln_w)[c4];
+    lb[c4] = reinterpret_cast<const float4*>(ln_b)[c4];
   }
-  float4 acc[NV];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int blk = blockIdx.x; blk * DW_ROWS_PER_CTA < M; blk += gridDim.x) {
+#pragma unroll 1
+    for (int r = 0; r < DW_ROWS_PER_CTA / 8; ++r) {
+      const int row = blk * DW_ROWS_PER_CTA + warp * (DW_ROWS_PER_CTA / 8) + r;
+      if (row >= M) break;
+      uint2* yr = reinterpret_cast<uint2*>(y + static_cast<size_t>(row) * ldy);
+      const int pos = row_pos[row];
+      if (pos < 0) {
 #pragma unroll
-  for (int i = 0; i < NV; ++i) acc[i] = reinterpret_cast<const float4*>(bias)[i * 32 + lane];
+        for (int i = 0; i < NV; ++i) yr[i * 32 + lane] = make_uint2(0, 0);
+        continue;
+      }
+      float4 acc[NV];
 #pragma unroll
-  for (int k = 0; k < 7; ++k) {
-    const int rr = row + k - 3;
-    if (rr < 0 || rr >= M) continue;
-    const int pr = row_pos[rr];
-    if (pr < 0 || pr != pos + k - 3) continue;  // gap row or another utterance => zero padding
-    const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(rr) * ldx);
+      for (int i = 0; i < NV; ++i) acc[i] = cb[i * 32 + lane];
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const float4 xv = xr[i * 32 + lane];
-      const int c = (i * 32 + lane) * 4;
-      acc[i].x += xv.x * w[(c + 0) * 7 + k];
-      acc[i].y += xv.y * w[(c + 1) * 7 + k];
-      acc[i].z += xv.z * w[(c + 2) * 7 + k];
-      acc[i].w += xv.w * w[(c + 3) * 7 + k];
+      for (int k = 0; k < 7; ++k) {
+        const int rr = row + k - 3;
+        if (rr < 0 || rr >= M) continue;
+        const int pr = row_pos[rr];
+        if (pr < 0 || pr != pos + k - 3) continue;  // gap row or another utterance => zero padding
+        const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(rr) * ldx);
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          const float4 xv = xr[i * 32 + lane];
+          const float4 wv = wT[k][i * 32 + lane];
+          acc[i].x = fmaf(xv.x, wv.x, acc[i].x);
+          acc[i].y = fmaf(xv.y, wv.y, acc[i].y);
+          acc[i].z = fmaf(xv.z, wv.z, acc[i].z);
+          acc[i].w = fmaf(xv.w, wv.w, acc[i].w);
+        }
+      }
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) s += (acc[i].x + acc[i].y) + (acc[i].z + acc[i].w);
+      const float mean = warp_sum(s) * (1.f / C);
+      float q = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const float d0 = acc[i].x - mean, d1 = acc[i].y - mean, d2 = acc[i].z - mean, d3 = acc[i].w - mean;
+        q += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+      }
+      const float rstd = rsqrtf(warp_sum(q) * (1.f / C) + eps);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const float4 a4 = lw[i * 32 + lane], b4 = lb[i * 32 + lane];
+        yr[i * 32 + lane] = make_uint2(
+            pack_bf16x2((acc[i].x - mean) * rstd * a4.x + b4.x, (acc[i].y - mean) * rstd * a4.y + b4.y),
+            pack_bf16x2((acc[i].z - mean) * rstd * a4.z + b4.z, (acc[i].w - mean) * rstd * a4.w + b4.w));
+      }
     }
-  }
-  float s = 0.f;
-#pragma unroll
-  for (int i = 0; i < NV; ++i) s += (acc[i].x + acc[i].y) + (acc[i].z + acc[i].w);
-  const float mean = warp_sum(s) * (1.f / C);
-  float q = 0.f;
-#pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const float d0 = acc[i].x - mean, d1 = acc[i].y - mean, d2 = acc[i].z - mean, d3 = acc[i].w - mean;
-    q += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
-  }
-  const float rstd = rsqrtf(warp_sum(q) * (1.f / C) + eps);
-#pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const float4 a4 = reinterpret_cast<const float4*>(ln_w)[i * 32 + lane];
-    const float4 b4 = reinterpret_cast<const float4*>(ln_b)[i * 32 + lane];
-    yr[i * 32 + lane] = make_uint2(
-        pack_bf16x2((acc[i].x - mean) * rstd * a4.x + b4.x, (acc[i].y - mean) * rstd * a4.y + b4.y),
-        pack_bf16x2((acc[i].z - mean) * rstd * a4.z + b4.z, (acc[i].w - mean) * rstd * a4.w + b4.w));
   }
 }
 
@@ -294,7 +314,8 @@ extern "C" int f5_dwconv7_ln(const float* x, int64_t ldx, void* y, int64_t ldy, 
                              void* stream) {
   if (!x || !y || !row_pos || !w || !bias || !ln_w || !ln_b || M <= 0 || C % 128 != 0 || C > 512 || ldx % 4 != 0 || ldy % 4 != 0)
     return F5_ERR_ARG;
-  const int grid = (M + 7) / 8;
+  const int blocks = (M + DW_ROWS_PER_CTA - 1) / DW_ROWS_PER_CTA;
+  const int grid = blocks < kNumSMsB200 * 8 ? blocks : kNumSMsB200 * 8;
   __nv_bfloat16* yo = reinterpret_cast<__nv_bfloat16*>(y);
   switch (C / 128) {
 #define F5_CASE(NV) case NV: dwconv7_ln_kernel<NV><<<grid, 256, 0, F5_STREAM(stream)>>>(x, ldx, yo, ldy, M, row_pos, w, bias, ln_w, ln_b, eps); break;

@@ -257,6 +257,21 @@ __device__ __forceinline__ float gelu_tanh_fast(float x) {
   const float t = c0 * (x + 0.044715f * x * x * x);
   return x * fast_rcp(1.f + fast_ex2(t));
 }
+// erf-GELU 0.5 x (1 + erf(x / sqrt 2)) with erf from Abramowitz-Stegun 7.1.26 (|error| < 1.5e-7 — three orders below the
+// bf16 rounding of the GEMM output it feeds): erf(z) = 1 - (a1 t + ... + a5 t^5) e^{-z^2}, t = 1 / (1 + p z), z >= 0.
+// One ex2 + one rcp instead of erff()'s ~40-instruction branchy polynomial: the K = 512 pointwise GEMMs of Vocos and of
+// the text ConvNeXt blocks are epilogue-bound (256 activations per thread per 4096-cycle tile).
+__device__ __forceinline__ float gelu_erf_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float t = fast_rcp(fmaf(0.3275911f, z, 1.f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float e = fast_ex2(-z * z * 1.4426950408889634f);
+  const float erf_abs = fmaf(-poly * t, e, 1.f);            // erf(|x| / sqrt 2)
+  return 0.5f * x + 0.5f * fabsf(x) * erf_abs;              // 0.5 x (1 + sign(x) erf_abs)
+}
 // x tanh(log(1+e^x)) == x n / (n + 2),  n = e^x (e^x + 2)
 __device__ __forceinline__ float mish_fast(float x) {
   const float e = fast_ex2(fminf(x, 20.f) * 1.4426950408889634f);

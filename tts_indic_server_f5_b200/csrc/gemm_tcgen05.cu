@@ -51,7 +51,7 @@ struct GemmParams {
 template <int ACT>
 __device__ __forceinline__ float apply_act(float v) {
   if constexpr (ACT == F5_ACT_GELU_TANH) return gelu_tanh_fast(v);
-  else if constexpr (ACT == F5_ACT_GELU_ERF) return gelu_erf(v);
+  else if constexpr (ACT == F5_ACT_GELU_ERF) return gelu_erf_fast(v);
   else if constexpr (ACT == F5_ACT_MISH) return mish_fast(v);
   else return v;
 }
