@@ -49,6 +49,12 @@ constexpr uint32_t ATT_TM_S = 0, ATT_TM_P = 256, ATT_TM_O = 384;   // column off
 #ifndef ATT_EXP_PIPE
 #define ATT_EXP_PIPE 0
 #endif
+#ifndef ATT_GATE_POS
+#define ATT_GATE_POS 0        // where group A opens the gate for QK_B of the same step: 0 after its row max, 1 / 2 after its first / second exp chunk
+#endif
+#ifndef ATT_DEFER_CHUNKS
+#define ATT_DEFER_CHUNKS 2   // exp chunks computed before waiting for the previous PV (their P stays in registers)
+#endif
 #ifndef ATT_POLY_PERIOD
 #define ATT_POLY_PERIOD 4
 #endif
@@ -378,7 +384,7 @@ attn_d64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnParams p
           alpha = fast_ex2(m_run - m_new);
           m_run = m_new;
         }
-        if (g == 0) mbar_arrive_a(b_gate);        // group B's scores for this step may be issued now (half-tile stagger)
+        if (ATT_GATE_POS == 0 && g == 0) mbar_arrive_a(b_gate);   // group B's scores for this step may be issued now (half-tile stagger)
         if (row == 0) F5_TRACE(2 + g, 8 * t + 2);
         // p = exp2(s*scale - m), row sum, P as packed bf16 pairs -> TMEM columns [c*16, c*16+16) of P_g.
         const float2 nm2 = make_float2(-m_run, -m_run);
@@ -403,8 +409,16 @@ attn_d64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnParams p
         // (ncu: 60 % of the tiles stalled ~300 cycles here when the wait came first).  Waiting on EVERY tile also keeps
         // this thread exactly one phase behind o_full (a parity wait must never fall two phases behind).
         uint32_t pk0[16], pk1[16];
+#if ATT_DEFER_CHUNKS >= 3
+        uint32_t pk2[16];
+#endif
         exp_chunk(0, pk0);
+        if (ATT_GATE_POS == 1 && g == 0) mbar_arrive_a(b_gate);
         exp_chunk(1, pk1);
+        if (ATT_GATE_POS == 2 && g == 0) mbar_arrive_a(b_gate);
+#if ATT_DEFER_CHUNKS >= 3
+        exp_chunk(2, pk2);
+#endif
         if (t > 0) {
           mbar_wait_a(b_o_full, (t - 1) & 1);
           tc_fence_after();
@@ -424,8 +438,11 @@ attn_d64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnParams p
         if (row == 0) F5_TRACE(2 + g, 8 * t + 3);
         tmem_st_32x32b_x16(tmem_P, pk0);
         tmem_st_32x32b_x16(tmem_P + 16, pk1);
+#if ATT_DEFER_CHUNKS >= 3
+        tmem_st_32x32b_x16(tmem_P + 32, pk2);
+#endif
 #pragma unroll
-        for (int c = 2; c < ATT_BN / 32; ++c) {
+        for (int c = ATT_DEFER_CHUNKS; c < ATT_BN / 32; ++c) {
           uint32_t pk[16];
           exp_chunk(c, pk);
           tmem_st_32x32b_x16(tmem_P + c * 16, pk);
