@@ -102,6 +102,33 @@ def test_gemm_resid_shapes(M, N, K, act, use_gate):
     assert torch.equal(x[M:], x0[M:]), "rows beyond M were touched"
 
 
+@pytest.mark.parametrize("M,N,K", [(37900, 512, 256), (38912, 1024, 1024), (45000, 256, 192)])
+def test_gemm_cluster_multicast(M, N, K):
+    """>= 296 M-blocks: the 256-wide GEMM runs as clusters of two CTAs that multicast halves of the weight tile to each other.
+    Odd and even numbers of M-blocks (a pair's second block beyond M), ragged last block, all three epilogue modes; the result
+    must also equal the single-CTA form bit for bit (same MMAs, same order)."""
+    A = rnd(M, K, seed=21, dtype=torch.bfloat16)
+    B = rnd(N, K, seed=22, scale=1 / math.sqrt(K), dtype=torch.bfloat16)
+    bias, gate, x0 = rnd(N, seed=23), rnd(N, seed=24), rnd(M, N, seed=25)
+    ref = A.float() @ B.float().t() + bias
+    out = torch.zeros(M, N, device=DEV, dtype=torch.bfloat16)
+    ops.gemm(A, B, mode=ops.F5_EPI_STORE_BF16, bias=bias, out=out)
+    x = x0.clone()
+    ops.gemm(A, B, mode=ops.F5_EPI_RESID_F32, bias=bias, gate=gate, resid=x)
+    o32 = torch.zeros(M, N, device=DEV)
+    ops.gemm(A, B, mode=ops.F5_EPI_STORE_F32, act=1, bias=bias, out=o32)
+    torch.cuda.synchronize()
+    check(f"cluster gemm bf16 {M}x{N}x{K}", out, ref, rel=4e-3)
+    check(f"cluster gemm resid {M}x{N}x{K}", x, x0 + gate * ref, rel=2e-5, amax=4e-4)
+    check(f"cluster gemm f32+gelu {M}x{N}x{K}", o32, F.gelu(ref, approximate="tanh"), rel=2e-5, amax=4e-4)
+    half = M // 2 // 128 * 128                       # < 296 M-blocks per call: the single-CTA kernel
+    out1 = torch.zeros(M, N, device=DEV, dtype=torch.bfloat16)
+    ops.gemm(A[:half], B, mode=ops.F5_EPI_STORE_BF16, bias=bias, out=out1[:half])
+    ops.gemm(A[half:], B, mode=ops.F5_EPI_STORE_BF16, bias=bias, out=out1[half:])
+    torch.cuda.synchronize()
+    assert torch.equal(out, out1)
+
+
 def test_gemm_qkv_rope():
     D, M = 256, 400
     A = rnd(M, D, seed=13, dtype=torch.bfloat16)

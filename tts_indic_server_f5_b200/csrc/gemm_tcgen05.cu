@@ -11,6 +11,7 @@
 // a few MB) stays L2-resident.
 #include "f5_common.cuh"
 #include "../../include/f5_b200.h"
+#include <cstdlib>
 
 namespace f5 {
 
@@ -59,7 +60,13 @@ __device__ __forceinline__ float apply_act(float v) {
 // named barrier 1: the four epilogue warps (128 threads)
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
-template <int BLOCK_N, int ACT>
+// CL = 2: the kernel runs as clusters of two CTAs that work on vertically adjacent tiles (M-blocks 2i and 2i+1 of the same
+// N-block).  Both need the same B (weight) tile for every k-block: each CTA fetches HALF of it and multicasts that half into
+// both CTAs' shared memory, so the L2 -> SM traffic per k-block drops from 16 + 32 KB to 16 + 16 KB per CTA (ncu: 16 TB/s of
+// L2 reads for the QKV GEMM, 58 % of the L2's peak and a large slice of the board's power budget).  A stage may be refilled
+// only when BOTH CTAs' MMAs have consumed it, so `empty` barriers count two arrivals and every stage release is a multicast
+// commit.  The MMAs themselves stay cta_group::1; nothing else in the roles changes.
+template <int BLOCK_N, int ACT, int CL>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_r, const GemmParams p) {
@@ -76,7 +83,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  // tile walk: unit u = first_unit, first_unit + num_walkers, ... ; CL = 1: unit = tile (m-block = u / num_n, n-fastest);
+  // CL = 2: unit = (pair of m-blocks, n-block), this CTA takes m-block 2 * (u / num_n) + rank (a pair's second block may lie
+  // beyond M: its loads are zero-filled and nothing is stored).
+  const int cta_rank = CL == 1 ? 0 : static_cast<int>(cluster_ctarank());
+  const int first_unit = static_cast<int>(blockIdx.x) / CL, num_walkers = static_cast<int>(gridDim.x) / CL;
+  const int num_tiles = ((p.num_m_tiles + CL - 1) / CL) * p.num_n_tiles;   // units
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -84,7 +96,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     if (p.resid_tma) tma_prefetch_desc(&tmap_r);
     for (int i = 0; i < Cfg::STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 1);
+      mbar_init(&empty_bar[i], CL);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
@@ -98,6 +110,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   }
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();            // the peer's barriers are initialised before anything can arrive on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
@@ -106,8 +119,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / p.num_n_tiles) * BLOCK_M;
+      for (int tile = first_unit; tile < num_tiles; tile += num_walkers) {
+        const int m0 = ((tile / p.num_n_tiles) * CL + cta_rank) * BLOCK_M;
         const int n0 = (tile % p.num_n_tiles) * BLOCK_N;
         for (int k = 0; k < p.num_k; ++k) {
           const int tap = k / p.kc_per_tap;
@@ -117,7 +130,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           uint8_t* sb = sa + Cfg::A_BYTES;
           mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
           tma_load_2d(sa, &tmap_a, &full_bar[stage], (p.a_grouped ? n0 : 0) + kc * BLOCK_K, m0 + tap - p.tap_pad);
-          tma_load_2d(sb, &tmap_b, &full_bar[stage], kc * BLOCK_K, tap * p.b_tap_rows + n0);
+          if (CL == 1) {
+            tma_load_2d(sb, &tmap_b, &full_bar[stage], kc * BLOCK_K, tap * p.b_tap_rows + n0);
+          } else {   // my half of the B tile (BLOCK_N / 2 rows), into both CTAs; the other half arrives from the peer
+            tma_load_2d_multicast(sb + cta_rank * (Cfg::B_BYTES / 2), &tmap_b, &full_bar[stage], kc * BLOCK_K,
+                                  tap * p.b_tap_rows + n0 + cta_rank * (BLOCK_N / 2), static_cast<uint16_t>(3));
+          }
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -130,7 +148,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = first_unit; tile < num_tiles; tile += num_walkers) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
@@ -145,7 +163,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             // advance 16 bf16 = 32 B along K inside the 128-B swizzle row: +2 in the (addr >> 4) field
             umma_f16_ss(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, (k | kk) != 0);
           }
-          umma_commit(&empty_bar[stage]);   // smem stage reusable once these MMAs retire
+          if (CL == 1) umma_commit(&empty_bar[stage]);   // smem stage reusable once these MMAs retire
+          else umma_commit_multicast(&empty_bar[stage], static_cast<uint16_t>(3));   // ... in BOTH CTAs (either may write it)
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
         umma_commit(&tmem_full[acc]);       // accumulator ready for the epilogue
@@ -167,8 +186,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const long long side_ld = p.mode == F5_EPI_RESID_F32 ? p.ldr : p.ld_add;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m0 = (tile / p.num_n_tiles) * BLOCK_M;
+    for (int tile = first_unit; tile < num_tiles; tile += num_walkers) {
+      const int m0 = ((tile / p.num_n_tiles) * CL + cta_rank) * BLOCK_M;
       const int n0 = (tile % p.num_n_tiles) * BLOCK_N;
       const int mw = m0 + quarter * 32;     // first row of this warp
       const bool rope_tile = p.rope != nullptr && (n0 % p.rope_period) == 0 && (n0 / p.rope_period) < p.rope_tiles;
@@ -379,6 +398,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();            // no CTA exits while its peer can still multicast into it or arrive on its barriers
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
@@ -435,13 +455,13 @@ int make_tmap_f32_2d_box32(CUtensorMap* map, const void* base, long long rows, l
   return r == CUDA_SUCCESS ? F5_OK : F5_ERR_DRIVER;
 }
 
-template <int BLOCK_N, int ACT>
+template <int BLOCK_N, int ACT, int CL>
 int launch_gemm(const f5_gemm_args& a, const GemmParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg<BLOCK_N>;
   CUtensorMap ta, tb, tr;
   int rc = make_tmap_bf16_2d(&ta, a.A, a.a_rows, a.a_cols, a.lda, BLOCK_M);
   if (rc != F5_OK) return rc;
-  rc = make_tmap_bf16_2d(&tb, a.B, a.b_rows, a.b_cols, a.ldb, BLOCK_N);
+  rc = make_tmap_bf16_2d(&tb, a.B, a.b_rows, a.b_cols, a.ldb, BLOCK_N / CL);   // CL = 2: each CTA loads half of the B tile
   if (rc != F5_OK) return rc;
   if (p.resid_tma) {
     rc = make_tmap_f32_2d_box32(&tr, a.resid, a.M, a.N, a.ldr);
@@ -451,16 +471,38 @@ int launch_gemm(const f5_gemm_args& a, const GemmParams& p, cudaStream_t stream)
   }
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BLOCK_N, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BLOCK_N, ACT, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return static_cast<int>(e);
     attr_set = true;
   }
   const int sms = a.num_sms > 0 ? a.num_sms : kNumSMsB200;
-  const int tiles = p.num_m_tiles * p.num_n_tiles;
-  const int grid = tiles < sms ? tiles : sms;
-  gemm_tcgen05_kernel<BLOCK_N, ACT><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, tr, p);
-  return static_cast<int>(cudaGetLastError());
+  const int units = ((p.num_m_tiles + CL - 1) / CL) * p.num_n_tiles;
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = CL > 1 ? 1 : 0;
+  int max_walkers = sms / CL;
+  if (CL > 1) {        // persistent kernel: no more clusters than the device can hold at once (a GPC with an odd SM count strands one)
+    static int max_clusters = -1;
+    if (max_clusters < 0) {
+      cfg.gridDim = dim3(kNumSMsB200);
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, gemm_tcgen05_kernel<BLOCK_N, ACT, CL>, &cfg) != cudaSuccess || n <= 0) n = sms / CL;
+      max_clusters = n;
+    }
+    if (max_clusters < max_walkers) max_walkers = max_clusters;
+  }
+  const int walkers = units < max_walkers ? units : max_walkers;
+  cfg.gridDim = dim3(walkers * CL);
+  return static_cast<int>(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<BLOCK_N, ACT, CL>, ta, tb, tr, p));
 }
 
 }  // namespace f5
@@ -505,15 +547,21 @@ extern "C" int f5_gemm_bf16(const f5_gemm_args* a, void* stream) {
   if (a->mask_rows && a->row_pos == nullptr) return F5_ERR_ARG;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   if (a->act < 0 || a->act > 3) return F5_ERR_ARG;
-#define F5_DISPATCH(BN)                                                        \
-  switch (a->act) {                                                            \
-    case F5_ACT_GELU_TANH: return launch_gemm<BN, F5_ACT_GELU_TANH>(*a, p, s); \
-    case F5_ACT_GELU_ERF: return launch_gemm<BN, F5_ACT_GELU_ERF>(*a, p, s);   \
-    case F5_ACT_MISH: return launch_gemm<BN, F5_ACT_MISH>(*a, p, s);           \
-    default: return launch_gemm<BN, F5_ACT_NONE>(*a, p, s);                    \
+#define F5_DISPATCH(BN, CL)                                                        \
+  switch (a->act) {                                                                \
+    case F5_ACT_GELU_TANH: return launch_gemm<BN, F5_ACT_GELU_TANH, CL>(*a, p, s); \
+    case F5_ACT_GELU_ERF: return launch_gemm<BN, F5_ACT_GELU_ERF, CL>(*a, p, s);   \
+    case F5_ACT_MISH: return launch_gemm<BN, F5_ACT_MISH, CL>(*a, p, s);           \
+    default: return launch_gemm<BN, F5_ACT_NONE, CL>(*a, p, s);                    \
   }
-  if (a->block_n == 256) { F5_DISPATCH(256) }
-  if (a->block_n == 128) { F5_DISPATCH(128) }
-  F5_DISPATCH(64)
+  // clusters of two CTAs sharing the weight tile: only where there are enough M-blocks for every SM pair (the big 256-wide
+  // layer GEMMs); F5_GEMM_CLUSTER=0 in the environment forces the single-CTA form (A/B measurements)
+  static const bool cluster_ok = [] { const char* e = getenv("F5_GEMM_CLUSTER"); return e == nullptr || e[0] != '0'; }();
+  if (a->block_n == 256) {
+    if (cluster_ok && !a->a_grouped && p.num_m_tiles >= 2 * kNumSMsB200) { F5_DISPATCH(256, 2) }
+    F5_DISPATCH(256, 1)
+  }
+  if (a->block_n == 128) { F5_DISPATCH(128, 1) }
+  F5_DISPATCH(64, 1)
 #undef F5_DISPATCH
 }
