@@ -227,7 +227,7 @@ def main():
 
     # ------------------------------------------------------------------ roofline of the dominant kernel (tcgen05 GEMM, BLOCK_N = 256)
     # One instrumented eager Euler step: CUDA events around every layer GEMM launch (QKV / out / FF1 / FF2, 22 layers).
-    recs, orig_gemm = [], ops.gemm
+    recs, arecs, orig_gemm, orig_attn = [], [], ops.gemm, ops.attention
 
     def timed_gemm(A, B, **kw):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -236,13 +236,20 @@ def main():
         b.record()
         recs.append((A.shape[0], kw.get("N") or B.shape[0], B.shape[1], kw.get("num_taps", 1), a, b))
 
+    def timed_attn(*a_, **kw):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        orig_attn(*a_, **kw)
+        b.record()
+        arecs.append((a, b))
+
     eng = model.engine
-    eng.use_graphs, ops.gemm = False, timed_gemm
+    eng.use_graphs, ops.gemm, ops.attention = False, timed_gemm, timed_attn
     try:
         eng.step(st.ws, 0, 2.0)
         torch.cuda.synchronize()
     finally:
-        eng.use_graphs, ops.gemm = True, orig_gemm
+        eng.use_graphs, ops.gemm, ops.attention = True, orig_gemm, orig_attn
     real_rows = 2 * st.layout.real_tokens                      # CFG pair; gap rows are not algorithmic work
     layer = [(N, K, a.elapsed_time(b) * 1e-3) for (M, N, K, taps, a, b) in recs if taps == 1 and N % 256 == 0 and K >= 1024]
     g_flops = sum(2.0 * real_rows * N * K for N, K, _ in layer)
@@ -252,17 +259,27 @@ def main():
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
-    peak_tf = peaks.get("bf16_tflops", 1590.0)
+    # the GEMMs are timed inside a live step of a run that has been loading the board for many seconds: the sustained peak
+    # is the denominator (the burst figure is kept alongside)
+    peak_tf = peaks.get("bf16_tflops_sustained", 1361.0)
+    burst_tf = peaks.get("bf16_tflops", 1590.0)
     traffic = None
     try:
         traffic = json.load(open(os.path.join(ROOT, "profiles", "gemm_traffic.json"))).get("dram_bytes_per_launch")
     except Exception:
         pass
     achieved = g_flops / g_time / 1e12 if g_time > 0 else 0.0
+    a_time = sum(a.elapsed_time(b) * 1e-3 for a, b in arecs)
+    a_flops = len(arecs) * 2.0 * sum(4.0 * 1024 * n * n for n in st.layout.lengths)    # QK^T + PV, both CFG halves, per layer
     roofline = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel<256> (QKV/out/FF1/FF2, 88 launches of one Euler step)",
                 "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-                "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst)" if peaks else "fallback 1.59 PFLOP/s",
-                "avg_launch_ms": g_time / max(len(layer), 1) * 1e3, "traffic": traffic}
+                "peak_source": ("MEASURED_PEAKS.json bf16_tflops_sustained (kernels timed with CUDA events inside one live Euler step "
+                                "right after the timed region)") if peaks else "fallback 1361 TFLOP/s sustained",
+                "frac_of_burst_peak": achieved / burst_tf, "burst_peak": burst_tf,
+                "avg_launch_ms": g_time / max(len(layer), 1) * 1e3, "traffic": traffic,
+                "secondary": {"kernel": "attn_d64_kernel (22 launches of the same step)", "bound": "mufu+tensor",
+                              "achieved": a_flops / a_time / 1e12 if a_time > 0 else 0.0, "unit": "TFLOP/s",
+                              "avg_launch_ms": a_time / max(len(arecs), 1) * 1e3}}
     total_flops = sum(flops_per_utterance(n, n - p.ref_len) for n, p in zip(st.layout.lengths, st.preps)) * world
     job_tflops = total_flops * args.steps / dt / 1e12 / world
     sustained = peaks.get("bf16_tflops_sustained", 1400.0)
