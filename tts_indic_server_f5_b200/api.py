@@ -303,7 +303,7 @@ class Synthesizer:
         preps = [self._prep(s, speed, fix_duration) for s in specs]
         mels: list = [None] * len(preps)
         h2d = 0
-        todo: dict[bytes, list[int]] = {}
+        todo: dict[tuple, list[int]] = {}
         for i, p in enumerate(preps):                                             # one mel per distinct prompt (voice cache)
             k = PromptCache.key(p.audio)
             m = self.prompt_cache.get(k, dev)

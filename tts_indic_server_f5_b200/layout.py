@@ -41,17 +41,18 @@ class PackedLayout:
 
 
 def build_layout(lengths: list[int], gap: int = GAP, both_halves: bool = True) -> PackedLayout:
-    starts, r = [], gap
-    for n in lengths:
-        assert n >= 1
-        starts.append(r)
-        r += n + gap
+    import numpy as np
+    lens = np.asarray(lengths, dtype=np.int64)
+    assert lens.ndim == 1 and lens.size >= 1 and (lens >= 1).all()
+    starts_np = gap + np.concatenate([[0], np.cumsum(lens[:-1] + gap)])
+    r = int(starts_np[-1] + lens[-1] + gap)
     R = (r + ROW_ALIGN - 1) // ROW_ALIGN * ROW_ALIGN
-    pos = torch.full((R,), -1, dtype=torch.int32)
-    utt = torch.full((R,), -1, dtype=torch.int32)
-    for i, (s, n) in enumerate(zip(starts, lengths)):
-        pos[s:s + n] = torch.arange(n, dtype=torch.int32)
-        utt[s:s + n] = i
+    pos_np = np.full(R, -1, dtype=np.int32)
+    utt_np = np.full(R, -1, dtype=np.int32)
+    rows = np.repeat(starts_np, lens) + (np.arange(int(lens.sum())) - np.repeat(np.cumsum(lens) - lens, lens))
+    pos_np[rows] = (rows - np.repeat(starts_np, lens)).astype(np.int32)
+    utt_np[rows] = np.repeat(np.arange(lens.size), lens).astype(np.int32)
+    starts = [int(x) for x in starts_np]
     halves = (0, R) if both_halves else (0,)
     tiles, segs = [], []
     for off in halves:
@@ -61,5 +62,6 @@ def build_layout(lengths: list[int], gap: int = GAP, both_halves: bool = True) -
                 tiles.append([off + s + q0, off + s, n, min(256, n - q0)])
     # longest-first ordering keeps the tail of the attention grid short
     tiles.sort(key=lambda t: -t[2])
-    return PackedLayout(list(lengths), starts, R, torch.cat([pos] * len(halves)), utt,
+    pos = torch.from_numpy(pos_np)
+    return PackedLayout(list(lengths), starts, R, torch.cat([pos] * len(halves)), torch.from_numpy(utt_np),
                         torch.tensor(tiles, dtype=torch.int32), torch.tensor(segs, dtype=torch.int32))
