@@ -243,6 +243,56 @@ def test_attention_many_items_per_cta():
     _attn_case([1219] * 6 + [1100] * 5, 16, scale_q=4.0, seed=34)
 
 
+def test_attention_properties_at_c2_size():
+    """Size-independent properties at the benchmark's own size (C2: 64 utterances x 2 CFG halves, 16 heads, 158 k rows) — no
+    reference needed: (1) softmax rows sum to one: with V == 1 every valid output is 1 up to the bf16 rounding of P;
+    (2) keys and values permuted together inside each utterance leave the output unchanged (up to bf16 rounding of P, whose
+    per-tile running max changes with the order); (3) gap rows are never written."""
+    from tts_indic_server_f5_b200.layout import build_layout
+    g = torch.Generator("cpu").manual_seed(0)
+    lens = [469 + int(torch.randint(560, 941, (1,), generator=g)) for _ in range(64)]
+    L = build_layout(lens)
+    H, D = 16, 1024
+    qkv = rnd(L.rows, 3 * D, seed=50, dtype=torch.bfloat16)
+    tiles = L.attn_tiles.to(DEV)
+    valid = (L.row_pos >= 0).to(DEV)
+    qkv1 = qkv.clone()
+    qkv1[:, 2 * D:] = 1.0
+    out = torch.full((L.rows, D), 7.0, device=DEV, dtype=torch.bfloat16)
+    ops.attention(qkv1, tiles, out, H, 0, D, 2 * D, 0.125)
+    torch.cuda.synchronize()
+    assert (out[valid].float() - 1.0).abs().max().item() <= 2 ** -6          # sum of ~1200 bf16-rounded probabilities / fp32 row sum
+    assert torch.all(out[~valid] == 7.0)                                      # gap rows untouched
+    base = torch.zeros(L.rows, D, device=DEV, dtype=torch.bfloat16)
+    ops.attention(qkv, tiles, base, H, 0, D, 2 * D, 0.125)
+    perm = torch.arange(L.rows)
+    for half in (0, L.half_rows):
+        for s0, n in zip(L.starts, lens):
+            perm[half + s0: half + s0 + n] = half + s0 + torch.randperm(n, generator=g)
+    qkvp = qkv.clone()
+    qkvp[:, D:] = qkv[perm.to(DEV), D:]                                       # K and V rows permuted, Q in place
+    outp = torch.zeros(L.rows, D, device=DEV, dtype=torch.bfloat16)
+    ops.attention(qkvp, tiles, outp, H, 0, D, 2 * D, 0.125)
+    torch.cuda.synchronize()
+    check("attn key-permutation invariance (C2 size)", outp[valid], base[valid], rel=6e-3)
+
+
+def test_gemm_linearity_at_c2_size():
+    """D(A1 + A2) == D(A1) + D(A2) at the layer-GEMM size of the benchmark (fp32 outputs, exact bf16 operands chosen so that
+    A1 + A2 is representable): exercises every tile, the cluster path and the TMA reduce epilogue (resid accumulates twice)."""
+    M, N, K = 158976, 1024, 1024
+    A1 = (torch.randint(-8, 9, (M, K), generator=torch.Generator().manual_seed(1)).float() / 8).to(DEV).to(torch.bfloat16)
+    A2 = (torch.randint(-8, 9, (M, K), generator=torch.Generator().manual_seed(2)).float() / 8).to(DEV).to(torch.bfloat16)
+    B = rnd(N, K, seed=3, scale=1 / 32, dtype=torch.bfloat16)
+    x12 = torch.zeros(M, N, device=DEV)
+    ops.gemm(A1, B, mode=ops.F5_EPI_RESID_F32, resid=x12)
+    ops.gemm(A2, B, mode=ops.F5_EPI_RESID_F32, resid=x12)
+    xs = torch.zeros(M, N, device=DEV)
+    ops.gemm((A1.float() + A2.float()).to(torch.bfloat16), B, mode=ops.F5_EPI_RESID_F32, resid=xs)
+    torch.cuda.synchronize()
+    check("gemm linearity (C2 size)", x12, xs, rel=1e-6, amax=1e-4)
+
+
 def test_layernorm_mod():
     for D in (128, 256, 512, 1024):
         M = 1001
