@@ -18,6 +18,8 @@
 //     of softmax_g(s) and S_g(s+1) is waiting in TMEM when softmax_g(s) ends — no QK round trip between tiles;
 //   * the step sequence is flat across work items: the first QK of the next item is issued during the last softmax of the
 //     current one (Q is refilled as soon as the item's last QK retired);
+//   * the first two 32-key chunks of exponentials are computed BEFORE the wait for the group's previous PV (their packed P
+//     stays in registers): only the tcgen05.st of P, the O rescale and the O read-out need that PV to have retired;
 //   * the O/l read-out of item i is deferred into the first softmax of item i+1 (after its row max, before its first P
 //     store), so the last PV's latency is hidden behind the S load and the max pass;
 //   * the two groups are kept HALF A TILE APART: QK_B(s) is only issued once group A has finished the row max of its
@@ -40,14 +42,8 @@ constexpr int ATT_KV_STAGES = 3;
 constexpr int ATT_SMEM = ATT_TILE_BYTES * (2 /*Q*/ + 2 * ATT_KV_STAGES /*K,V*/) + 256;
 constexpr int ATT_TMEM_COLS = 512;
 constexpr uint32_t ATT_TM_S = 0, ATT_TM_P = 256, ATT_TM_O = 384;   // column offsets; per group: + g*128 / g*64 / g*64
-#ifndef ATT_EXP_BF16X2
-#define ATT_EXP_BF16X2 0    // 1: ex2.approx.ftz.bf16x2 (two exponentials per MUFU op); A/B switch, see tools/attn_bench.py
-#endif
 #ifndef ATT_POLY_COUNT
 #define ATT_POLY_COUNT 1      // of every ATT_POLY_PERIOD score pairs, this many take the polynomial exp2 path (FMA pipes) instead of the MUFU
-#endif
-#ifndef ATT_EXP_PIPE
-#define ATT_EXP_PIPE 0
 #endif
 #ifndef ATT_GATE_POS
 #define ATT_GATE_POS 0        // where group A opens the gate for QK_B of the same step: 0 after its row max, 1 / 2 after its first / second exp chunk

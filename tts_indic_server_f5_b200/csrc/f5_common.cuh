@@ -302,12 +302,6 @@ __device__ __forceinline__ float mish_fast(float x) {
   const float n = e * (e + 2.f);
   return x * n * fast_rcp(n + 2.f);
 }
-// two bf16 exponentials in one MUFU op
-__device__ __forceinline__ uint32_t ex2_bf16x2(uint32_t x) {
-  uint32_t y;
-  asm("ex2.approx.ftz.bf16x2 %0, %1;" : "=r"(y) : "r"(x));
-  return y;
-}
 // packed 2-wide fp32 (sm_100: FFMA2 / FADD2 halve the issue slots of the softmax inner loop)
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
   float2 d;
