@@ -190,6 +190,35 @@ def test_request_scheduler_equals_per_request_calls(tiny_models, tmp_path):
         np.testing.assert_array_equal(out[rid][2], mel)
 
 
+def test_step_graph_is_reused_across_lengths(tiny_models):
+    """The captured 32-step graph depends on the packed row count and the padded attention item count only: a batch of other
+    utterance lengths that packs into the same rows REPLAYS it (the tile table, positions, noise, prompt are buffer contents),
+    and the replay is bit-identical to a fresh engine that captures its own graph for that batch."""
+    cfg, vcfg, sd, vsd, model, voc = tiny_models
+    syn = api.Synthesizer(model, voc)
+
+    def specs_for(gens):
+        out = []
+        for i, g_ in enumerate(gens):
+            sp = S.workload("tiny3")[i % 3]
+            sp.duration = sp.meta["ref_len"] + g_
+            out.append(sp)
+        return out
+
+    a = specs_for([150, 200, 170])
+    b = specs_for([155, 195, 170])            # other lengths, same total rows after 128-row padding, same padded item count
+    syn.generate(a)
+    eng = model.engine
+    c0, r0 = eng.graph_captures, eng.graph_replays
+    wb = syn.generate(b)
+    assert (eng.graph_captures, eng.graph_replays) == (c0, r0 + 1), "a new length signature must not re-capture the step graph"
+    fresh = api.Synthesizer(api.load_model(state_dict=sd), voc)
+    for x, y in zip(wb, fresh.generate(b)):
+        np.testing.assert_array_equal(x, y)
+    syn.generate(a)                           # and back
+    assert eng.graph_captures == c0
+
+
 def test_istft_perfect_reconstruction_property():
     """Size-independent property of the ISTFT kernels: analysing a signal with the matching STFT and feeding
     (log|X|, angle X) back reconstructs the signal (hann, hop = n_fft/4 satisfies COLA)."""

@@ -57,7 +57,7 @@ constexpr uint32_t ATT_TM_S = 0, ATT_TM_P = 256, ATT_TM_O = 384;   // column off
 
 struct AttnParams {
   int q_col, k_col, v_col, heads;
-  const int* items;   // [num_pairs][4] = q_row0, kv_row0, kv_len, q_rows_valid (1..256)
+  const int* items;   // [num_pairs][4] = q_row0, kv_row0, kv_len, q_rows_valid (1..256; 0 = padding item, skipped)
   int num_work;       // num_pairs * heads
   __nv_bfloat16* out;
   long long ldo;
@@ -108,12 +108,14 @@ struct StepWalker {
       : items(p.items), num_work(p.num_work), heads(p.heads), w(static_cast<int>(blockIdx.x)), j(0) { load(); }
   __device__ __forceinline__ bool valid() const { return w < num_work; }
   __device__ __forceinline__ void load() {
-    if (w < num_work) {
+    while (w < num_work) {                              // items with no query rows are padding of the tile table: skip them
       it = *reinterpret_cast<const int4*>(items + 4 * (w / heads));
-      head = w % heads;
-      nkv = (it.z + ATT_BN - 1) / ATT_BN;
-      ngroups = it.w > ATT_BM ? 2 : 1;
+      if (it.w > 0 && it.z > 0) break;
+      w += static_cast<int>(gridDim.x);
     }
+    head = w % heads;
+    nkv = (it.z + ATT_BN - 1) / ATT_BN;
+    ngroups = it.w > ATT_BM ? 2 : 1;
   }
   __device__ __forceinline__ bool last_tile() const { return j + 1 == nkv; }
   __device__ __forceinline__ void next() {
@@ -338,7 +340,7 @@ attn_d64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnParams p
       const int4 it = *reinterpret_cast<const int4*>(p.items + 4 * (w / p.heads));
       const int head = w % p.heads;
       const int q_valid = it.w - g * ATT_BM;      // rows of this group's tile that exist
-      if (q_valid <= 0) continue;                 // tile B absent: the MMA warp skips this group too
+      if (q_valid <= 0 || it.z <= 0) continue;    // tile B absent / padding item: the MMA warp skips it too
       const int kv_len = it.z;
       const int nkv = (kv_len + ATT_BN - 1) / ATT_BN;
       float m_run = -INFINITY, l_run = 0.f;

@@ -163,6 +163,11 @@ class Workspace:
         self.mod = z(steps_pad, (6 * L + 2) * D, F32)
         self.tgrid = torch.zeros(steps_pad + 1, device=device, dtype=F32)
         self.dts = torch.zeros(steps_pad, device=device, dtype=F32)
+        # attention work items live in ONE device buffer per workspace: the captured step graph holds its address and the
+        # (padded) item count, so batches of other utterance lengths that fit the same rows replay the same graph
+        self.tiles_buf = torch.zeros(2 * (R // 128 + 64), 4, device=device, dtype=I32)
+        self.graphs: dict[tuple, torch.cuda.CUDAGraph] = {}
+        self.graph_launches: dict[tuple, int] = {}
 
 
 class F5Engine:
@@ -182,15 +187,20 @@ class F5Engine:
         self.cfg, self.device = cfg, dev
         self.w = DiTWeights(sd, cfg, self.device)
         self.use_graphs = use_graphs
-        self._ws: dict[int, Workspace] = {}
-        self._graphs: dict[tuple, torch.cuda.CUDAGraph] = {}
-        self._tables: dict[tuple, tuple] = {}
+        self._ws: dict[int, Workspace] = {}          # LRU over row counts (insertion order = recency)
+        self.max_workspaces = 4                       # ~30 KB of buffers per row: C2 (159 k rows) is 4.7 GB
+        self.max_graphs_per_workspace = 8
+        self.graph_captures = 0                       # statistics: captures vs replays of the step graph
+        self.graph_replays = 0
 
     # ------------------------------------------------------------------------------------------ batch set-up
     def workspace(self, R: int) -> Workspace:
-        ws = self._ws.get(R)
+        ws = self._ws.pop(R, None)
         if ws is None:
-            ws = self._ws[R] = Workspace(self.cfg, R, 128, self.device)
+            while len(self._ws) >= self.max_workspaces:            # evict the least recently used size (and its graphs)
+                self._ws.pop(next(iter(self._ws)))
+            ws = Workspace(self.cfg, R, 128, self.device)
+        self._ws[R] = ws
         return ws
 
     def upload(self, utts: list[UtteranceInput], layout: PackedLayout, steps: int, sway: float | None) -> Workspace:
@@ -227,12 +237,16 @@ class F5Engine:
         ws.ids.copy_(h_ids, non_blocking=True)
         ws.cond_flag.copy_(h_flag, non_blocking=True)
         ws.row_pos.copy_(layout.row_pos.pin_memory(), non_blocking=True)
-        key = layout.signature()
-        tabs = self._tables.get(key)
-        if tabs is None:
-            tabs = (layout.attn_tiles.to(self.device), layout.seg_rows.to(self.device))
-            self._tables = {key: tabs}          # keep only the latest (tables are tiny; avoids unbounded growth)
-        ws.tiles, ws.segs = tabs
+        n_items = layout.attn_tiles.shape[0]
+        padded = (n_items + 7) // 8 * 8                # item count is baked into the step graph: pad it to a multiple of 8 ...
+        if padded > ws.tiles_buf.shape[0]:
+            ws.tiles_buf = torch.zeros(padded + 64, 4, device=self.device, dtype=I32)
+            ws.graphs.clear()
+        h_tiles = torch.zeros(padded, 4, dtype=I32).pin_memory()   # ... with items of zero query rows, which the kernel skips
+        h_tiles[:n_items] = layout.attn_tiles
+        ws.tiles_buf[:padded].copy_(h_tiles, non_blocking=True)
+        ws.tiles = ws.tiles_buf[:padded]
+        ws.segs = layout.seg_rows.to(self.device, non_blocking=True)
         ws.sumsq = torch.zeros(ws.segs.shape[0], cfg.text_inner, device=self.device, dtype=F32)
         t = sway_time_grid(steps, sway)
         h_t = pin(ws.tgrid.shape[0])
@@ -303,12 +317,15 @@ class F5Engine:
         ops.cfg_euler(ws.x, ws.pred, R, cfg.mel_dim, ws.row_pos, ws.dts, s, cfg_strength, ws.xb, MELP)
 
     def run_steps(self, ws: Workspace, steps: int, cfg_strength: float) -> None:
-        key = (ws.R, ws.tiles.shape[0], ws.segs.shape[0], steps, float(cfg_strength), ws.tiles.data_ptr())
+        # The graph bakes in addresses of this workspace's buffers and the launch parameters: row count (the workspace), padded
+        # attention item count, steps, cfg.  Everything else a batch changes — lengths, positions, tile table, noise, prompt,
+        # text — is CONTENT of those buffers, so any batch that packs into the same rows replays the same graph.
+        key = (ws.tiles.shape[0], steps, float(cfg_strength), ws.tiles.data_ptr())
         if not self.use_graphs:
             for s in range(steps):
                 self.step(ws, s, cfg_strength)
             return
-        g = self._graphs.get(key)
+        g = ws.graphs.pop(key, None)
         if g is None:
             x_saved = ws.x.clone()
             self.step(ws, 0, cfg_strength)            # eager warm-up of every kernel variant (sets func attributes) ...
@@ -318,14 +335,19 @@ class F5Engine:
             with torch.cuda.graph(g):                 # capture records, it does not execute
                 for s in range(steps):
                     self.step(ws, s, cfg_strength)
-            self._graph_launches = _lib.launch_count - n0
+            ws.graph_launches[key] = _lib.launch_count - n0
             _lib.launch_count = n0
             ws.x.copy_(x_saved)                       # ... then restore the state the warm-up step advanced
             ops.pack_bf16(ws.x, ws.xb, 0, self.cfg.mel_dim, MELP, row_pos=ws.row_pos, M=ws.R)
             ops.pack_bf16(ws.x, ws.xb[ws.R:], 0, self.cfg.mel_dim, MELP, row_pos=ws.row_pos, M=ws.R)
-            self._graphs = {key: g}                   # one live graph (its node arguments point into this workspace)
+            while len(ws.graphs) >= self.max_graphs_per_workspace:
+                ws.graphs.pop(next(iter(ws.graphs)))
+            self.graph_captures += 1
+        else:
+            self.graph_replays += 1
+        ws.graphs[key] = g                            # most recently used last
         g.replay()
-        _lib.launch_count += self._graph_launches
+        _lib.launch_count += ws.graph_launches[key]
 
     # ------------------------------------------------------------------------------------------ public
     @torch.inference_mode()
