@@ -20,8 +20,16 @@ def _ld(t: torch.Tensor) -> int:
     return t.stride(0)
 
 
-def pick_block_n(N: int) -> int:
+def pick_block_n(N: int, M: int | None = None) -> int:
+    """Tile width of the persistent GEMM.  256 is the efficient shape (one A tile feeds 256 columns); for small M — a single
+    utterance is 13 row blocks — it leaves most of the 148 SMs idle or pays a nearly empty second wave, so the narrower tile
+    wins when it needs fewer `waves x tile width` (the K loop is the same)."""
     if N % 256 == 0:
+        if M is not None:
+            mt = (M + 127) // 128
+            cost = lambda bn, eff: -(-(mt * (N // bn)) // 148) * bn * eff      # noqa: E731  ceil(tiles / SMs) * width
+            if cost(128, 1.08) < cost(256, 1.0):
+                return 128
         return 256
     if N >= 128:
         return 128
@@ -41,7 +49,7 @@ def gemm(A: torch.Tensor, B: torch.Tensor, *, M: int | None = None, N: int | Non
     a.b_rows, a.b_cols = B.shape
     a.M = A.shape[0] if M is None else M
     a.N = (B.shape[0] if num_taps == 1 else b_tap_rows) if N is None else N
-    a.block_n = block_n or pick_block_n(a.N)
+    a.block_n = block_n or pick_block_n(a.N, a.M)
     a.num_taps = num_taps
     a.kc_per_tap = kc_per_tap if kc_per_tap is not None else (B.shape[1] + 63) // 64
     a.tap_pad, a.a_grouped, a.b_tap_rows = tap_pad, int(a_grouped), b_tap_rows
