@@ -116,34 +116,45 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // The WHOLE warp walks the loops (warp-uniform control flow keeps coordinates / addresses in uniform registers, which
+    // is what UTMALDG / UTCHMMA consume); only the TMA / MMA / commit instructions are predicated on one elected lane.
+    // Issued from inside a divergent `if (lane == 0)` region every such instruction pays a serial R2UR chain (~85 cycles,
+    // measured in the attention kernel): hidden under the 512 tensor cycles of a 256-wide k-block, but 2.2x the 192 cycles
+    // of a 64-wide one — the grouped conv ran at 145 cycles per MMA against the 48 its shape allows.
+    {
+      const bool leader = elect_one();
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = first_unit; tile < num_tiles; tile += num_walkers) {
         const int m0 = ((tile / p.num_n_tiles) * CL + cta_rank) * BLOCK_M;
         const int n0 = (tile % p.num_n_tiles) * BLOCK_N;
+        int tap = 0, kc = 0;
         for (int k = 0; k < p.num_k; ++k) {
-          const int tap = k / p.kc_per_tap;
-          const int kc = k - tap * p.kc_per_tap;
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + Cfg::A_BYTES;
-          mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-          tma_load_2d(sa, &tmap_a, &full_bar[stage], (p.a_grouped ? n0 : 0) + kc * BLOCK_K, m0 + tap - p.tap_pad);
-          if (CL == 1) {
-            tma_load_2d(sb, &tmap_b, &full_bar[stage], kc * BLOCK_K, tap * p.b_tap_rows + n0);
-          } else {   // my half of the B tile (BLOCK_N / 2 rows), into both CTAs; the other half arrives from the peer
-            tma_load_2d_multicast(sb + cta_rank * (Cfg::B_BYTES / 2), &tmap_b, &full_bar[stage], kc * BLOCK_K,
-                                  tap * p.b_tap_rows + n0 + cta_rank * (BLOCK_N / 2), static_cast<uint16_t>(3));
+          if (leader) {
+            mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+            tma_load_2d(sa, &tmap_a, &full_bar[stage], (p.a_grouped ? n0 : 0) + kc * BLOCK_K, m0 + tap - p.tap_pad);
+            if (CL == 1) {
+              tma_load_2d(sb, &tmap_b, &full_bar[stage], kc * BLOCK_K, tap * p.b_tap_rows + n0);
+            } else {   // my half of the B tile (BLOCK_N / 2 rows), into both CTAs; the other half arrives from the peer
+              tma_load_2d_multicast(sb + cta_rank * (Cfg::B_BYTES / 2), &tmap_b, &full_bar[stage], kc * BLOCK_K,
+                                    tap * p.b_tap_rows + n0 + cta_rank * (BLOCK_N / 2), static_cast<uint16_t>(3));
+            }
           }
+          __syncwarp();
+          if (++kc == p.kc_per_tap) { kc = 0; ++tap; }
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // ------------------------------------------------------------ MMA issuer (warp-uniform, see the producer)
+    {
+      const bool leader = elect_one();
       constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M, BLOCK_N);
+      const uint64_t desc0 = umma_desc_k_sw128(smem_u32(smem));
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -155,19 +166,22 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         for (int k = 0; k < p.num_k; ++k) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-          const uint64_t adesc = umma_desc_k_sw128(sa);
-          const uint64_t bdesc = umma_desc_k_sw128(sa + Cfg::A_BYTES);
+          const uint64_t adesc = desc0 + static_cast<uint64_t>(stage) * (Cfg::STAGE_BYTES >> 4);   // address field is in 16-B units
+          const uint64_t bdesc = adesc + (Cfg::A_BYTES >> 4);
+          if (leader) {
 #pragma unroll
-          for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk) {
-            // advance 16 bf16 = 32 B along K inside the 128-B swizzle row: +2 in the (addr >> 4) field
-            umma_f16_ss(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, (k | kk) != 0);
+            for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk) {
+              // advance 16 bf16 = 32 B along K inside the 128-B swizzle row: +2 in the (addr >> 4) field
+              umma_f16_ss(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, idesc, (k | kk) != 0);
+            }
+            if (CL == 1) umma_commit(&empty_bar[stage]);   // smem stage reusable once these MMAs retire
+            else umma_commit_multicast(&empty_bar[stage], static_cast<uint16_t>(3));   // ... in BOTH CTAs (either may write it)
           }
-          if (CL == 1) umma_commit(&empty_bar[stage]);   // smem stage reusable once these MMAs retire
-          else umma_commit_multicast(&empty_bar[stage], static_cast<uint16_t>(3));   // ... in BOTH CTAs (either may write it)
+          __syncwarp();
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tmem_full[acc]);       // accumulator ready for the epilogue
+        if (leader) umma_commit(&tmem_full[acc]);       // accumulator ready for the epilogue
+        __syncwarp();
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
