@@ -181,31 +181,45 @@ attn_d64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnParams p
    if (warp == 8) {
     // ------------------------------------------------------------------ TMA producer
     // Issue order per step s:  Q_A(item) | K(s) | Q_B(item) | V(s-1)  — the order the MMA warp consumes them in.
-    if (lane == 0) {
+    // The whole warp walks the loop; only the TMA instructions are predicated on one elected lane (uniform registers).
+    {
+      const bool leader = elect_one();
       uint32_t item_a = 0, item_b = 0, s = 0;
       int v_col = 0, v_row = 0;
       auto load_v = [&](uint32_t sv_step) {
         const uint32_t sv = sv_step % ATT_KV_STAGES, pv = (sv_step / ATT_KV_STAGES) & 1;
         mbar_wait(&v_empty[sv], pv ^ 1);
-        mbar_expect_tx(&v_full[sv], ATT_TILE_BYTES);
-        tma_load_2d(sV + sv * ATT_TILE_BYTES, &tmap_qkv, &v_full[sv], v_col, v_row);
+        if (leader) {
+          mbar_expect_tx(&v_full[sv], ATT_TILE_BYTES);
+          tma_load_2d(sV + sv * ATT_TILE_BYTES, &tmap_qkv, &v_full[sv], v_col, v_row);
+        }
+        __syncwarp();
       };
       for (StepWalker c(p); c.valid(); c.next(), ++s) {
         if (c.j == 0) {
           mbar_wait(&q_empty[0], (item_a & 1) ^ 1);            // previous item's last QK_A has retired
-          mbar_expect_tx(&q_full[0], ATT_TILE_BYTES);
-          tma_load_2d(sQ, &tmap_qkv, &q_full[0], p.q_col + c.head * ATT_D, c.it.x);
+          if (leader) {
+            mbar_expect_tx(&q_full[0], ATT_TILE_BYTES);
+            tma_load_2d(sQ, &tmap_qkv, &q_full[0], p.q_col + c.head * ATT_D, c.it.x);
+          }
+          __syncwarp();
           ++item_a;
         }
         const uint32_t st = s % ATT_KV_STAGES, ph = (s / ATT_KV_STAGES) & 1;
         mbar_wait(&k_empty[st], ph ^ 1);
-        mbar_expect_tx(&k_full[st], ATT_TILE_BYTES);
-        tma_load_2d(sK + st * ATT_TILE_BYTES, &tmap_qkv, &k_full[st], p.k_col + c.head * ATT_D, c.it.y + c.j * ATT_BN);
-        F5_TRACE(0, s);
+        if (leader) {
+          mbar_expect_tx(&k_full[st], ATT_TILE_BYTES);
+          tma_load_2d(sK + st * ATT_TILE_BYTES, &tmap_qkv, &k_full[st], p.k_col + c.head * ATT_D, c.it.y + c.j * ATT_BN);
+        }
+        __syncwarp();
+        if (lane == 0) { F5_TRACE(0, s); }
         if (c.j == 0 && c.ngroups == 2) {
           mbar_wait(&q_empty[1], (item_b & 1) ^ 1);            // group B's previous item's last QK_B has retired
-          mbar_expect_tx(&q_full[1], ATT_TILE_BYTES);
-          tma_load_2d(sQ + ATT_TILE_BYTES, &tmap_qkv, &q_full[1], p.q_col + c.head * ATT_D, c.it.x + ATT_BM);
+          if (leader) {
+            mbar_expect_tx(&q_full[1], ATT_TILE_BYTES);
+            tma_load_2d(sQ + ATT_TILE_BYTES, &tmap_qkv, &q_full[1], p.q_col + c.head * ATT_D, c.it.x + ATT_BM);
+          }
+          __syncwarp();
           ++item_b;
         }
         if (s > 0) load_v(s - 1);

@@ -193,6 +193,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     // float4 per unit.  All side loads are issued a unit ahead: with ~210 KB of smem carved out the L1 is tiny, so a
     // dependent global load on the critical path costs an L2 round trip.
     const int quarter = warp & 3;           // TMEM lane quarter this warp may access
+    const bool epi_leader = elect_one();    // the lane that issues (and later waits for) this warp's TMA reduces
     uint8_t* stg = stage_base + (warp - 2) * 8192;
     const int rd_row = lane >> 3, rd_chunk = lane & 7;
     constexpr int UNITS = BLOCK_N / 32;
@@ -332,7 +333,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             mbar_arrive(&tmem_empty[acc]);
           }
           uint8_t* buf = stg + (u & 1) * 4096;
-          if (lane == 0) bulk_wait_group_read<1>();        // the reduce that last read this buffer (two units ago) is done with it
+          if (epi_leader) bulk_wait_group_read<1>();        // the reduce that last read this buffer (two units ago) is done with it
           __syncwarp();
           if (n0 + u * 32 < p.N) {                         // warp-uniform
 #pragma unroll
@@ -348,7 +349,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             }
             fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) {
+            if (epi_leader) {
               tma_reduce_add_2d(&tmap_r, buf, n0 + u * 32, mw);   // rows >= M / cols >= N are clipped by the tensor map
               bulk_commit_group();
             }
@@ -407,7 +408,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       mbar_arrive(&tmem_empty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
-    if (p.resid_tma && lane == 0) bulk_wait_group<0>();   // every reduce-add of this warp has completed
+    if (p.resid_tma && epi_leader) bulk_wait_group<0>();   // every reduce-add of this warp has completed
   }
 
   tc_fence_before();
