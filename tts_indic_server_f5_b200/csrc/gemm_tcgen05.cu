@@ -264,7 +264,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             }
             if constexpr (ACT != F5_ACT_NONE) {
 #pragma unroll
-              for (int j = 0; j < 64; ++j) v[j] = apply_act<ACT>(v[j]);
+              for (int j = 0; j < 64; j += 2) {
+                if constexpr (ACT == F5_ACT_GELU_TANH) {
+                  const float2 g2 = gelu_tanh_fast2(make_float2(v[j], v[j + 1]));
+                  v[j] = g2.x; v[j + 1] = g2.y;
+                } else {
+                  v[j] = apply_act<ACT>(v[j]); v[j + 1] = apply_act<ACT>(v[j + 1]);
+                }
+              }
             }
             if (rope_tile && u == 0 && pos >= 0) {
               // interleaved-pair rotation of head 0 (x-transformers apply_rotary_pos_emb; model/modules.py:418-419)
