@@ -38,7 +38,10 @@ constexpr int ATT_BM = 128;   // query rows per tile (two tiles per work item)
 constexpr int ATT_BN = 128;   // keys per tile
 constexpr int ATT_D = 64;
 constexpr int ATT_TILE_BYTES = 128 * 64 * 2;  // 16 KB
-constexpr int ATT_KV_STAGES = 3;
+#ifndef ATT_KV_STAGES_N
+#define ATT_KV_STAGES_N 3
+#endif
+constexpr int ATT_KV_STAGES = ATT_KV_STAGES_N;   // stages of the K ring and of the V ring (<= 4: barrier slots)
 constexpr int ATT_SMEM = ATT_TILE_BYTES * (2 /*Q*/ + 2 * ATT_KV_STAGES /*K,V*/) + 256;
 constexpr int ATT_TMEM_COLS = 512;
 constexpr uint32_t ATT_TM_S = 0, ATT_TM_P = 256, ATT_TM_O = 384;   // column offsets; per group: + g*128 / g*64 / g*64
