@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(256) dwconv7_ln_kernel(const float* __restrict
   for (int blk = blockIdx.x; blk * DW_ROWS_PER_CTA < M; blk += gridDim.x) {
 #pragma unroll 1
     for (int r = 0; r < DW_ROWS_PER_CTA / 8; ++r) {
-      const int row = blk * DW_ROWS_PER_CTA + warp * (DW_ROWS_PER_CTA / 8) + r;
+      const int row = blk * DW_ROWS_PER_CTA + r * 8 + warp;   // the 8 warps work on 8 ADJACENT rows at a time (halo rows shared in L1)
       if (row >= M) break;
       uint2* yr = reinterpret_cast<uint2*>(y + static_cast<size_t>(row) * ldy);
       const int pos = row_pos[row];
