@@ -23,6 +23,8 @@ import torch
 
 _CUSTOM_TRANS = str.maketrans({";": ",", "“": '"', "”": '"', "‘": "'", "’": "'"})  # utils.py:142-144
 _ASCII_RUN = re.compile(r"[a-zA-Z0-9]+(?:\.\d+)?%?")
+# anything the character scan treats specially: Han, or an ASCII alphanumeric that starts a multi-character _ASCII_RUN match
+_NEEDS_SCAN = re.compile(r"[\u3100-\u9fff]|[a-zA-Z0-9](?:[a-zA-Z0-9]|\.\d|%)")
 
 
 def get_tokenizer(vocab_file: str, tokenizer: str = "custom"):
@@ -62,6 +64,9 @@ def convert_char_to_pinyin(text_list: list[str], polyphone: bool = True) -> list
     out = []
     for text in text_list:
         text = text.translate(_CUSTOM_TRANS)
+        if _NEEDS_SCAN.search(text) is None:      # no Han, no run of >= 2 ASCII alphanumerics (pure Indic text): one token
+            out.append(list(text))                # per code point — the scan below would append exactly these
+            continue
         chars: list[str] = []
         i = 0
         while i < len(text):
