@@ -36,6 +36,21 @@ def test_tokenizer_one_token_per_codepoint_and_vocab_roundtrip(tmp_path):
     assert T.convert_char_to_pinyin(["ಕ;ab"])[0] == ["ಕ", ",", " ", "a", "b"]   # ';'->',' and ASCII-run leading space
 
 
+def test_tokenizer_fast_path_equals_character_scan(monkeypatch):
+    """Pure-Indic text takes a fast path (one token per code point); it must equal the full character scan of
+    utils.py:140-177 on arbitrary mixtures of Indic code points, punctuation, quotes, digits, decimals and percent signs."""
+    import random
+    import re
+    from tts_indic_server_f5_b200 import text as T
+    rng = random.Random(0)
+    alphabet = [chr(c) for c in range(0x0C80, 0x0CA0)] + list(" .,;!?:'\"%") + list("ab7Z09") + ["\u201c", "\u2019"]
+    strings = ["".join(rng.choice(alphabet) for _ in range(rng.randint(1, 30))) for _ in range(3000)]
+    fast = T.convert_char_to_pinyin(strings)
+    monkeypatch.setattr(T, "_NEEDS_SCAN", re.compile(""))          # always scan
+    assert T.convert_char_to_pinyin(strings) == fast
+    assert any(T._ASCII_RUN.search(s) for s in strings)
+
+
 def test_duration_and_ref_text_rules():
     assert T.finish_ref_text("abc") == "abc. " and T.finish_ref_text("abc.") == "abc. " and T.finish_ref_text("abc. ") == "abc. "
     assert T.estimate_duration(468, "x" * 100, "y" * 50) == 468 + 234
