@@ -335,6 +335,23 @@ __device__ __forceinline__ float2 gelu_tanh_fast2(float2 x) {
   e = fadd2(e, make_float2(1.f, 1.f));
   return fmul2(x, make_float2(fast_rcp(e.x), fast_rcp(e.y)));
 }
+// gelu_erf_fast on a pair (packed polynomial; |x| via sign-bit masks)
+__device__ __forceinline__ float2 gelu_erf_fast2(float2 x) {
+  const float2 ax = make_float2(fabsf(x.x), fabsf(x.y));
+  const float2 z = fmul2(ax, make_float2(0.70710678118654752f, 0.70710678118654752f));
+  const float2 d = ffma2(z, make_float2(0.3275911f, 0.3275911f), make_float2(1.f, 1.f));
+  const float2 t = make_float2(fast_rcp(d.x), fast_rcp(d.y));
+  float2 p = ffma2(t, make_float2(1.061405429f, 1.061405429f), make_float2(-1.453152027f, -1.453152027f));
+  p = ffma2(p, t, make_float2(1.421413741f, 1.421413741f));
+  p = ffma2(p, t, make_float2(-0.284496736f, -0.284496736f));
+  p = ffma2(p, t, make_float2(0.254829592f, 0.254829592f));
+  const float2 zz = fmul2(z, make_float2(-1.4426950408889634f * z.x, -1.4426950408889634f * z.y));   // -z^2 log2(e)
+  const float2 e = make_float2(fast_ex2(zz.x), fast_ex2(zz.y));
+  const float2 pt = fmul2(p, t);
+  const float2 erf_abs = ffma2(make_float2(-pt.x, -pt.y), e, make_float2(1.f, 1.f));                 // erf(|x| / sqrt 2)
+  const float2 hx = fmul2(x, make_float2(0.5f, 0.5f));
+  return ffma2(make_float2(0.5f * ax.x, 0.5f * ax.y), erf_abs, hx);                                  // 0.5 x + 0.5 |x| erf_abs
+}
 // exp2 on the FMA/ALU pipes for a pair of values (Cody-Waite split + degree-3 minimax polynomial, rel. error ~1e-4 — far
 // below the bf16 rounding of P).  Used for a fraction of the softmax exponentials so that the MUFU (16 ex2/clk/SM) is not
 // the only unit doing them.  Inputs must be <= ~100; they are clamped at -126 (2^-126 stands in for exp2(-inf) = 0).

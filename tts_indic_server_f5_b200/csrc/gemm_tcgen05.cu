@@ -268,6 +268,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 if constexpr (ACT == F5_ACT_GELU_TANH) {
                   const float2 g2 = gelu_tanh_fast2(make_float2(v[j], v[j + 1]));
                   v[j] = g2.x; v[j + 1] = g2.y;
+                } else if constexpr (ACT == F5_ACT_GELU_ERF) {
+                  const float2 g2 = gelu_erf_fast2(make_float2(v[j], v[j + 1]));
+                  v[j] = g2.x; v[j + 1] = g2.y;
                 } else {
                   v[j] = apply_act<ACT>(v[j]); v[j + 1] = apply_act<ACT>(v[j + 1]);
                 }
