@@ -18,7 +18,7 @@ namespace f5 {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;   // 64 bf16 = 128 B = one swizzle row
 constexpr int UMMA_K = 16;
-constexpr int GEMM_THREADS = 192;
+// block size: 6 warps (producer, MMA, 4 epilogue) or, with EW = 8, 12 (producer, MMA, 2 idle, 8 epilogue)
 
 template <int BLOCK_N>
 struct GemmCfg {
@@ -57,8 +57,9 @@ __device__ __forceinline__ float apply_act(float v) {
   else return v;
 }
 
-// named barrier 1: the four epilogue warps (128 threads)
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+// named barrier 1: the epilogue warps (EW x 32 threads)
+template <int EW>
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory"); }
 
 // CL = 2: the kernel runs as clusters of two CTAs that work on vertically adjacent tiles (M-blocks 2i and 2i+1 of the same
 // N-block).  Both need the same B (weight) tile for every k-block: each CTA fetches HALF of it and multicasts that half into
@@ -66,8 +67,13 @@ __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;"
 // L2 reads for the QKV GEMM, 58 % of the L2's peak and a large slice of the board's power budget).  A stage may be refilled
 // only when BOTH CTAs' MMAs have consumed it, so `empty` barriers count two arrivals and every stage release is a multicast
 // commit.  The MMAs themselves stay cta_group::1; nothing else in the roles changes.
-template <int BLOCK_N, int ACT, int CL>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+// EW = 8 (bf16-store GEMMs with 256-wide tiles AND an activation: FF1, the text / Vocos pointwise convs): eight epilogue warps, two per TMEM lane quarter, each taking half
+// of the tile's columns.  One epilogue warp per scheduler issues ~36 % of the time and is latency-bound (tmem load ->
+// activation -> smem round trip -> stores per 64-column unit): FF1 with its GELU held the tensor pipe at 67 %.  The block is
+// three warpgroups (producer / MMA / 2 idle warps, then the two epilogue warpgroups) so that setmaxnreg can move the
+// producer warpgroup's registers to the epilogue (56 / 224).
+template <int BLOCK_N, int ACT, int CL, int EW>
+__global__ void __launch_bounds__((EW == 8 ? 12 : 6) * 32, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_r, const GemmParams p) {
   using Cfg = GemmCfg<BLOCK_N>;
@@ -100,7 +106,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 128);
+      mbar_init(&tmem_empty[i], EW * 32);
     }
     mbar_fence_init();
   }
@@ -114,6 +120,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
+  constexpr int EPI_W0 = EW == 8 ? 4 : 2;    // first epilogue warp
+  if (warp < EPI_W0) {
+  if constexpr (EW == 8) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     // The WHOLE warp walks the loops (warp-uniform control flow keeps coordinates / addresses in uniform registers, which
@@ -185,8 +194,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
+  }
   } else {
-    // ------------------------------------------------------------ epilogue (warps 2..5)
+    if constexpr (EW == 8) asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    // ------------------------------------------------------------ epilogue (warps 2..5, or 4..11 when EW == 8)
     // Per 32-column unit: TMEM -> registers (thread = row) -> raw fp32 into a per-warp 4 KB staging tile (32 rows x 128 B,
     // 16-B chunks XOR-swizzled by row) -> read back with 8 lanes per row, so every global access (bf16/fp32 stores, the
     // fp32 residual read-modify-write, addend, bias, gate, RoPE table) is coalesced and each lane needs ONE bias/gate
@@ -194,7 +205,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     // dependent global load on the critical path costs an L2 round trip.
     const int quarter = warp & 3;           // TMEM lane quarter this warp may access
     const bool epi_leader = elect_one();    // the lane that issues (and later waits for) this warp's TMA reduces
-    uint8_t* stg = stage_base + (warp - 2) * 8192;
+    const int col_half = EW == 8 ? (warp - EPI_W0) >> 2 : 0;      // EW == 8: which half of the tile's columns this warp owns
+    uint8_t* stg = stage_base + (warp - EPI_W0) * (EW == 8 ? 4096 : 8192);
+    if (EW == 8 && p.mode != F5_EPI_STORE_BF16) __trap();          // the 8-warp form is instantiated for the bf16-store epilogue only
     const int rd_row = lane >> 3, rd_chunk = lane & 7;
     constexpr int UNITS = BLOCK_N / 32;
     const float* side = p.mode == F5_EPI_RESID_F32 ? p.resid : (p.mode == F5_EPI_STORE_F32 ? p.addend : nullptr);
@@ -232,8 +245,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         // bf16 outputs: 64-column units (one full 128-B line per row), math in the thread = row layout, the tile's bias slice
         // served from a per-warp smem copy (fetched before the accumulator wait).
         float* bias_s = bias_base;
-        epi_bar_sync();                                    // every epilogue warp is done with the previous tile's slice
-        for (int c = (threadIdx.x - 64) * 4; c < BLOCK_N; c += 512) {
+        epi_bar_sync<EW>();                                    // every epilogue warp is done with the previous tile's slice
+        for (int c = (static_cast<int>(threadIdx.x) - EPI_W0 * 32) * 4; c < BLOCK_N; c += EW * 128) {
           const float4 b = (p.bias != nullptr && n0 + c < p.N) ? *reinterpret_cast<const float4*>(p.bias + n0 + c)
                                                                : make_float4(0.f, 0.f, 0.f, 0.f);
           *reinterpret_cast<float4*>(bias_s + c) = b;
@@ -241,11 +254,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         const int m = mw + lane;
         const int pos = (p.row_pos != nullptr && m < p.M) ? p.row_pos[m] : 0;
         const bool zero_row = p.mask_rows && pos < 0;
-        epi_bar_sync();
+        epi_bar_sync<EW>();
         mbar_wait(&tmem_full[acc], acc_phase);
         tc_fence_after();
+        constexpr int U_PER_WARP = (BLOCK_N / 64) / (EW == 8 ? 2 : 1);
 #pragma unroll 1
-        for (int u = 0; u < BLOCK_N / 64; ++u) {
+        for (int u = col_half * U_PER_WARP; u < (col_half + 1) * U_PER_WARP; ++u) {
           uint32_t r0[32], r1[32];
           tmem_ld_32x32b_x32(taddr + u * 64, r0);
           tmem_ld_32x32b_x32(taddr + u * 64 + 32, r1);
@@ -322,15 +336,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         // ~45 KB the HBM latency-bandwidth product needs, so the K = 1024 out-projection ran at half of either roofline.
         float* bias_s = bias_base;
         float* gate_s = bias_base + BLOCK_N;
-        epi_bar_sync();
-        for (int c = (threadIdx.x - 64) * 4; c < BLOCK_N; c += 512) {
+        epi_bar_sync<EW>();
+        for (int c = (static_cast<int>(threadIdx.x) - EPI_W0 * 32) * 4; c < BLOCK_N; c += EW * 128) {
           const bool cok = n0 + c < p.N;
           *reinterpret_cast<float4*>(bias_s + c) = (p.bias != nullptr && cok) ? *reinterpret_cast<const float4*>(p.bias + n0 + c)
                                                                                : make_float4(0.f, 0.f, 0.f, 0.f);
           *reinterpret_cast<float4*>(gate_s + c) = (p.gate != nullptr && cok) ? *reinterpret_cast<const float4*>(p.gate + n0 + c)
                                                                                : make_float4(1.f, 1.f, 1.f, 1.f);
         }
-        epi_bar_sync();
+        epi_bar_sync<EW>();
         mbar_wait(&tmem_full[acc], acc_phase);
         tc_fence_after();
 #pragma unroll 1
@@ -480,7 +494,7 @@ int make_tmap_f32_2d_box32(CUtensorMap* map, const void* base, long long rows, l
   return r == CUDA_SUCCESS ? F5_OK : F5_ERR_DRIVER;
 }
 
-template <int BLOCK_N, int ACT, int CL>
+template <int BLOCK_N, int ACT, int CL, int EW = 4>
 int launch_gemm(const f5_gemm_args& a, const GemmParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg<BLOCK_N>;
   CUtensorMap ta, tb, tr;
@@ -496,7 +510,7 @@ int launch_gemm(const f5_gemm_args& a, const GemmParams& p, cudaStream_t stream)
   }
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BLOCK_N, ACT, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BLOCK_N, ACT, CL, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return static_cast<int>(e);
     attr_set = true;
@@ -504,7 +518,7 @@ int launch_gemm(const f5_gemm_args& a, const GemmParams& p, cudaStream_t stream)
   const int sms = a.num_sms > 0 ? a.num_sms : kNumSMsB200;
   const int units = ((p.num_m_tiles + CL - 1) / CL) * p.num_n_tiles;
   cudaLaunchConfig_t cfg = {};
-  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.blockDim = dim3((EW == 8 ? 12 : 6) * 32);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -520,14 +534,14 @@ int launch_gemm(const f5_gemm_args& a, const GemmParams& p, cudaStream_t stream)
     if (max_clusters < 0) {
       cfg.gridDim = dim3(kNumSMsB200);
       int n = 0;
-      if (cudaOccupancyMaxActiveClusters(&n, gemm_tcgen05_kernel<BLOCK_N, ACT, CL>, &cfg) != cudaSuccess || n <= 0) n = sms / CL;
+      if (cudaOccupancyMaxActiveClusters(&n, gemm_tcgen05_kernel<BLOCK_N, ACT, CL, EW>, &cfg) != cudaSuccess || n <= 0) n = sms / CL;
       max_clusters = n;
     }
     if (max_clusters < max_walkers) max_walkers = max_clusters;
   }
   const int walkers = units < max_walkers ? units : max_walkers;
   cfg.gridDim = dim3(walkers * CL);
-  return static_cast<int>(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<BLOCK_N, ACT, CL>, ta, tb, tr, p));
+  return static_cast<int>(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<BLOCK_N, ACT, CL, EW>, ta, tb, tr, p));
 }
 
 }  // namespace f5
@@ -582,8 +596,26 @@ extern "C" int f5_gemm_bf16(const f5_gemm_args* a, void* stream) {
   // clusters of two CTAs sharing the weight tile: only where there are enough M-blocks for every SM pair (the big 256-wide
   // layer GEMMs); F5_GEMM_CLUSTER=0 in the environment forces the single-CTA form (A/B measurements)
   static const bool cluster_ok = [] { const char* e = getenv("F5_GEMM_CLUSTER"); return e == nullptr || e[0] != '0'; }();
+  static const bool ew8_ok = [] { const char* e = getenv("F5_GEMM_EW8"); return e == nullptr || e[0] != '0'; }();
   if (a->block_n == 256) {
-    if (cluster_ok && !a->a_grouped && p.num_m_tiles >= 2 * kNumSMsB200) { F5_DISPATCH(256, 2) }
+    const bool cl2 = cluster_ok && !a->a_grouped && p.num_m_tiles >= 2 * kNumSMsB200;
+    // eight epilogue warps where the epilogue carries an activation (measured: FF1 + tanh-GELU 557 -> 532 us, but a plain bf16
+    // store gets 2-6 % SLOWER with the larger block); F5_GEMM_EW8=0 forces four
+    if (ew8_ok && a->mode == F5_EPI_STORE_BF16 && a->act != F5_ACT_NONE) {
+      if (cl2) {
+        switch (a->act) {
+          case F5_ACT_GELU_TANH: return launch_gemm<256, F5_ACT_GELU_TANH, 2, 8>(*a, p, s);
+          case F5_ACT_GELU_ERF: return launch_gemm<256, F5_ACT_GELU_ERF, 2, 8>(*a, p, s);
+          default: return launch_gemm<256, F5_ACT_MISH, 2, 8>(*a, p, s);
+        }
+      }
+      switch (a->act) {
+        case F5_ACT_GELU_TANH: return launch_gemm<256, F5_ACT_GELU_TANH, 1, 8>(*a, p, s);
+        case F5_ACT_GELU_ERF: return launch_gemm<256, F5_ACT_GELU_ERF, 1, 8>(*a, p, s);
+        default: return launch_gemm<256, F5_ACT_MISH, 1, 8>(*a, p, s);
+      }
+    }
+    if (cl2) { F5_DISPATCH(256, 2) }
     F5_DISPATCH(256, 1)
   }
   if (a->block_n == 128) { F5_DISPATCH(128, 1) }
