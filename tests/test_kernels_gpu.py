@@ -129,6 +129,26 @@ def test_gemm_cluster_multicast(M, N, K):
     assert torch.equal(out, out1)
 
 
+@pytest.mark.parametrize("M", [515, 38017])
+@pytest.mark.parametrize("act", [1, 2, 3])
+def test_gemm_store_bf16_activation_eight_epilogue_warps(M, act):
+    """bf16-store GEMMs with an activation and 256-wide tiles run eight epilogue warps (two per TMEM lane quarter, each half of
+    the tile's columns), alone (M = 515) and inside two-CTA clusters (M = 38017: 298 M-blocks, ragged last block)."""
+    N, K = 768, 320
+    A = rnd(M, K, seed=31, dtype=torch.bfloat16)
+    B = rnd(N, K, seed=32, scale=1 / math.sqrt(K), dtype=torch.bfloat16)
+    bias = rnd(N, seed=33)
+    row_pos = torch.arange(M, device=DEV, dtype=torch.int32)
+    row_pos[40:56] = -1
+    out = torch.full((M, N), 5.0, device=DEV, dtype=torch.bfloat16)
+    ops.gemm(A, B, mode=ops.F5_EPI_STORE_BF16, act=act, bias=bias, out=out, row_pos=row_pos, mask_rows=True)
+    torch.cuda.synchronize()
+    z = A.float() @ B.float().t() + bias
+    z = [z, F.gelu(z, approximate="tanh"), F.gelu(z), F.mish(z)][act]
+    z[40:56] = 0
+    check(f"gemm bf16 act{act} M={M}", out, z, rel=4e-3)
+
+
 def test_gemm_qkv_rope():
     D, M = 256, 400
     A = rnd(M, D, seed=13, dtype=torch.bfloat16)
