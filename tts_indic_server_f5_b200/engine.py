@@ -242,11 +242,11 @@ class F5Engine:
         if padded > ws.tiles_buf.shape[0]:
             ws.tiles_buf = torch.zeros(padded + 64, 4, device=self.device, dtype=I32)
             ws.graphs.clear()
-        h_tiles = torch.zeros(padded, 4, dtype=I32).pin_memory()   # ... with items of zero query rows, which the kernel skips
+        h_tiles = torch.zeros(padded, 4, dtype=I32)                # ... with items of zero query rows, which the kernel skips
         h_tiles[:n_items] = layout.attn_tiles
-        ws.tiles_buf[:padded].copy_(h_tiles, non_blocking=True)
+        ws.tiles_buf[:padded].copy_(h_tiles)                       # a few KB: plain blocking copies (no host-buffer lifetime to reason about)
         ws.tiles = ws.tiles_buf[:padded]
-        ws.segs = layout.seg_rows.to(self.device, non_blocking=True)
+        ws.segs = layout.seg_rows.to(self.device)
         ws.sumsq = torch.zeros(ws.segs.shape[0], cfg.text_inner, device=self.device, dtype=F32)
         t = sway_time_grid(steps, sway)
         h_t = pin(ws.tgrid.shape[0])
