@@ -322,14 +322,93 @@ def main():
         dist.destroy_process_group()
 
 
+def _fake_worker() -> None:
+    """Stand-in for the measurement (tests/test_bench_supervisor.py, CPU only): F5_BENCH_FAKE = "fail=<rank>" makes that rank's
+    worker die on the first attempt; every other worker blocks (as a rank stuck in a collective would) until it is killed or,
+    on a healthy attempt, prints the JSON line on rank 0."""
+    spec = os.environ["F5_BENCH_FAKE"]
+    rank, attempt = int(os.environ.get("RANK", "0")), int(os.environ.get("F5_BENCH_ATTEMPT", "0"))
+    failing = int(spec.split("=")[1]) if spec.startswith("fail=") else -1
+    if attempt == 0 and failing >= 0:
+        if rank == failing:
+            time.sleep(1.0)
+            sys.stderr.write(f"fake worker rank {rank}: simulated launch failure\n")
+            sys.exit(3)
+        time.sleep(600.0)                       # stuck in the collective the dead rank never joins
+    time.sleep(0.5)
+    if spec == "pg":                            # a real process group on the child's own rendezvous port (gloo; the product uses nccl)
+        import torch.distributed as dist
+        dist.init_process_group("gloo")
+        t = torch.tensor([float(rank + 1)])
+        dist.all_reduce(t)
+        assert float(t) == sum(range(1, dist.get_world_size() + 1))
+        dist.destroy_process_group()
+    if rank == 0:
+        emit({"metric": METRIC, "value": 1.0, "unit": UNIT, "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "fake": True,
+              "attempt": attempt, "master_port": os.environ.get("MASTER_PORT")})
+
+
+def supervise_ranks() -> int:
+    """Multi-rank runs (launched by torchrun): this process supervises the real measurement, which runs in a child process
+    with its own rendezvous port.  A rank that dies (a CUDA launch failure is sticky for its process) cannot be restarted
+    alone — its peers are inside NCCL collectives — so the supervisors agree through a small TCPStore: as soon as one child
+    fails, every supervisor kills its child, and all ranks start ONE fresh attempt together.  Rank 0 forwards its child's
+    JSON line.  Single-GPU runs use the simpler in-place restart below."""
+    import datetime
+    import subprocess
+    from torch.distributed import TCPStore
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    addr = os.environ.get("MASTER_ADDR", "127.0.0.1")
+    base_port = int(os.environ.get("MASTER_PORT", "29500"))
+    for attempt in range(2):
+        env = dict(os.environ)
+        env.update(F5_BENCH_WORKER="1", F5_BENCH_ATTEMPT=str(attempt), MASTER_PORT=str(base_port + 20 + attempt))
+        env.pop("TORCHELASTIC_USE_AGENT_STORE", None)   # the children rendezvous on their OWN port: rank 0's child hosts that store
+        store = TCPStore(addr, base_port + 10 + attempt, world, is_master=(rank == 0), timeout=datetime.timedelta(seconds=900),
+                         wait_for_workers=False)
+        child = subprocess.Popen([sys.executable, os.path.abspath(__file__)] + sys.argv[1:], env=env, stdout=subprocess.PIPE)
+        deadline = time.time() + 1500.0
+        while child.poll() is None:
+            if store.check(["abort"]) or time.time() > deadline:
+                child.kill()
+                break
+            time.sleep(0.5)
+        out = child.stdout.read()
+        rc = child.wait()
+        ok = rc == 0 and (rank != 0 or out.strip().startswith(b"{"))
+        if not ok:
+            store.set("abort", "1")
+        store.set(f"done{rank}", "1" if ok else "0")
+        store.wait([f"done{r}" for r in range(world)])
+        all_ok = all(store.get(f"done{r}") == b"1" for r in range(world))
+        store.set(f"seen{rank}", "1")           # nobody tears the store down while a peer still reads it
+        store.wait([f"seen{r}" for r in range(world)])
+        if all_ok:
+            if rank == 0:
+                os.write(_REAL_STDOUT, out if out.endswith(b"\n") else out + b"\n")
+            return 0
+        sys.stderr.write(f"bench: attempt {attempt} failed on some rank (rank {rank}: rc={rc}); "
+                         f"{'restarting all ranks' if attempt == 0 else 'giving up'}\n")
+        del store
+        time.sleep(3.0)
+    return 1
+
+
 if __name__ == "__main__":
+    _multi = int(os.environ.get("WORLD_SIZE", "1")) > 1
+    _worker = os.environ.get("F5_BENCH_WORKER") == "1"
+    if _multi and not _worker and "reference" not in sys.argv and os.environ.get("F5_BENCH_NO_SUPERVISOR") is None:
+        sys.exit(supervise_ranks())
+    if os.environ.get("F5_BENCH_FAKE") is not None:
+        _fake_worker()
+        sys.exit(0)
     try:
         main()
     except Exception:
         import traceback
         traceback.print_exc()
-        # one clean re-start of a single-GPU run (a fresh process and CUDA context); multi-rank runs are left to the launcher
-        if int(os.environ.get("WORLD_SIZE", "1")) == 1 and os.environ.get("F5_BENCH_RETRIED") is None:
+        # one clean re-start of a single-GPU run (a fresh process and CUDA context); multi-rank runs restart through supervise_ranks
+        if not _multi and os.environ.get("F5_BENCH_RETRIED") is None:
             sys.stderr.write("bench: measurement failed, restarting once in a fresh process\n")
             sys.stderr.flush()
             os.environ["F5_BENCH_RETRIED"] = "1"
