@@ -21,15 +21,10 @@ def _ld(t: torch.Tensor) -> int:
 
 
 def pick_block_n(N: int, M: int | None = None) -> int:
-    """Tile width of the persistent GEMM.  256 is the efficient shape (one A tile feeds 256 columns); for small M — a single
-    utterance is 13 row blocks — it leaves most of the 148 SMs idle or pays a nearly empty second wave, so the narrower tile
-    wins when it needs fewer `waves x tile width` (the K loop is the same)."""
+    """Tile width of the persistent GEMM: 256 wherever N allows (one A tile feeds 256 columns).  An M-aware choice (narrower
+    tiles when 256-wide ones leave SMs idle on small batches) was measured at a single utterance and bought 1 ms of 65:
+    not worth a second kernel configuration on the hot path."""
     if N % 256 == 0:
-        if M is not None:
-            mt = (M + 127) // 128
-            cost = lambda bn, eff: -(-(mt * (N // bn)) // 148) * bn * eff      # noqa: E731  ceil(tiles / SMs) * width
-            if cost(128, 1.08) < cost(256, 1.0):
-                return 128
         return 256
     if N >= 128:
         return 128
