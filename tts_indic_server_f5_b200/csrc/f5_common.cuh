@@ -83,7 +83,8 @@ __device__ __forceinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
       if (t0 == 0) t0 = now;
       if (now - t0 > F5_WATCHDOG_CYCLES) {
 #if F5_WATCHDOG_PRINT
-        printf("f5: mbarrier watchdog: block %d thread %d bar %u parity %u\n", blockIdx.x, threadIdx.x, bar, parity);
+        printf("f5: mbarrier watchdog: grid %d x %d threads, block %d thread %d, barrier at smem %u parity %u\n", gridDim.x,
+               blockDim.x, blockIdx.x, threadIdx.x, bar, parity);
 #endif
         __trap();
       }
