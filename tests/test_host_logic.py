@@ -208,3 +208,34 @@ def test_engine_refuses_to_run_without_cuda():
         api.load_model(device="cpu")
     with pytest.raises(RuntimeError):
         api.load_model(device="cuda")
+
+
+def test_wav_response_matches_a_wav_reader():
+    """Response body format of `synthesize_speech` (tts_utils.py:60-65): 24 kHz mono 16-bit PCM WAV, int16 input rescaled
+    by 1/32768 first.  Read back with the stdlib `wave` module and, when present, with soundfile (the reference's writer)."""
+    import wave
+    from tts_indic_server_f5_b200.api import wav_response_bytes
+    rng = np.random.default_rng(0)
+    x = (0.3 * rng.standard_normal(24000)).astype(np.float32)
+    x[:4] = [1.5, -1.5, 1.0, -1.0]                                   # out-of-range samples clip, full scale maps to +-32767
+    buf = wav_response_bytes(x)
+    with wave.open(buf, "rb") as w:
+        assert (w.getframerate(), w.getnchannels(), w.getsampwidth(), w.getnframes()) == (24000, 1, 2, 24000)
+        pcm = np.frombuffer(w.readframes(24000), dtype="<i2")
+    assert pcm[:4].tolist() == [32767, -32767, 32767, -32767]
+    assert np.array_equal(pcm, np.rint(np.clip(x.astype(np.float64), -1, 1) * 32767).astype(np.int16))
+    # the int16 return type of the model object goes through the same 1/32768 rescale as the server applies
+    xi = (x[4:] * 32768).astype(np.int16)
+    with wave.open(wav_response_bytes(xi), "rb") as w:
+        pcm_i = np.frombuffer(w.readframes(w.getnframes()), dtype="<i2")
+    assert np.abs(pcm_i.astype(np.int32) - xi.astype(np.int32)).max() <= 1
+    with pytest.raises(ValueError):
+        wav_response_bytes(np.zeros((2, 10), np.float32))
+    try:
+        import soundfile as sf
+    except Exception:
+        return
+    import io
+    ref = io.BytesIO()
+    sf.write(ref, x[4:], 24000, format="WAV")
+    assert ref.getvalue() == wav_response_bytes(x[4:]).getvalue()

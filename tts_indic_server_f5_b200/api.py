@@ -459,3 +459,27 @@ class TTSManager:
         if not self.model:
             raise ValueError("TTS model not loaded")
         return self.model(text, ref_audio_path=ref_audio_path, ref_text=ref_text)
+
+
+def wav_response_bytes(audio: np.ndarray, sample_rate: int = target_sample_rate) -> "io.BytesIO":
+    """Response body of `synthesize_speech` (src/server/utils/tts_utils.py:60-65): an int16 array is rescaled by 1/32768,
+    then the float wave is written as a RIFF/WAVE file, which libsndfile's default for format='WAV' stores as 16-bit PCM
+    (sample = round-to-nearest-even of x * 32767).  Samples outside [-1, 1] are clipped here; libsndfile without
+    SFC_SET_CLIPPING wraps them, which is audible garbage and not a behaviour worth matching.  Header layout is the
+    canonical 44-byte PCM one (the same bytes `sf.write` emits for mono PCM_16)."""
+    import io
+    import struct
+    a = np.asarray(audio)
+    if a.ndim != 1:
+        raise ValueError("mono 1-D audio expected")
+    if a.dtype == np.int16:
+        a = a.astype(np.float32) / 32768.0
+    pcm = np.rint(np.clip(a.astype(np.float64), -1.0, 1.0) * 32767.0).astype("<i2")
+    data = pcm.tobytes()
+    buf = io.BytesIO()
+    buf.write(b"RIFF" + struct.pack("<I", 36 + len(data)) + b"WAVE")
+    buf.write(b"fmt " + struct.pack("<IHHIIHH", 16, 1, 1, sample_rate, sample_rate * 2, 2, 16))
+    buf.write(b"data" + struct.pack("<I", len(data)))
+    buf.write(data)
+    buf.seek(0)
+    return buf
