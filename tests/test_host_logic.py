@@ -239,3 +239,27 @@ def test_wav_response_matches_a_wav_reader():
     ref = io.BytesIO()
     sf.write(ref, x[4:], 24000, format="WAV")
     assert ref.getvalue() == wav_response_bytes(x[4:]).getvalue()
+
+
+def test_sample_prologue_rules():
+    """`CFM.sample` prologue (cfm.py:118-137, :181-186) as host logic: lens = max(text_lens, lens); duration =
+    clamp(max(lens + 1, duration), <= max_duration); one noise draw per item re-seeded with the same seed (so items share
+    a noise prefix); pad ids (-1) stripped.  Runs without a GPU on a stub of the engine-backed object."""
+    from types import SimpleNamespace
+    from tts_indic_server_f5_b200.api import CFM
+    stub = SimpleNamespace(vocab_char_map={" ": 0, "a": 1, "b": 2}, num_channels=100, _device="cpu")
+    cond = torch.randn(3, 40, 100)
+    text = torch.tensor([[1, 2, 1, -1, -1, -1], [1] * 6, [2, 2, -1, -1, -1, -1]])
+    utts = CFM._prepare(stub, cond, text, torch.tensor([30, 100, 5000]), torch.tensor([40, 3, 40]), 7, 4096, None, None)
+    assert [u.n for u in utts] == [41, 100, 4096]                 # lens + 1 floor, as given, clamped to max_duration
+    assert [u.cond_len for u in utts] == [40, 6, 40]              # item 1: text_lens (6) > lens (3)
+    assert [u.text_ids.tolist() for u in utts] == [[1, 2, 1], [1] * 6, [2, 2]]
+    # shared seed => shared noise prefix (torch's CPU normal_ recomputes the last 16 values of a draw, so up to those)
+    assert torch.equal(utts[0].y0.flatten()[:-16], utts[1].y0.flatten()[:4100 - 16])
+    assert torch.equal(utts[1].y0.flatten()[:-16], utts[2].y0.flatten()[:10000 - 16])
+    torch.manual_seed(7)
+    assert torch.equal(utts[2].y0, torch.randn(4096, 100))
+    # an int duration broadcasts; strings go through the vocabulary (unknown -> 0)
+    utts = CFM._prepare(stub, cond[:1], ["abz"], 64, None, None, 4096, None, [torch.ones(80, 100)])
+    assert utts[0].n == 64 and utts[0].cond_len == 40 and utts[0].text_ids.tolist() == [1, 2, 0]
+    assert utts[0].y0.shape == (64, 100) and bool((utts[0].y0 == 1).all())
