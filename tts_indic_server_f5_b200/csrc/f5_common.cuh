@@ -7,12 +7,14 @@
 #include <stdint.h>
 #include <cstdio>
 
-#ifndef F5_WATCHDOG_CYCLES
-// ~25 s at 1.5 GHz: a stuck pipeline traps instead of hanging the GPU.  It was 2 s until a handful of bench runs (4 of ~50,
-// clustered in time on particular boxes, under ncu too) died with "unspecified launch failure" in otherwise healthy code: the
-// only trap in these kernels is this watchdog, and anything that stops the SM clock's owner for a couple of seconds
-// (profiler pauses, a co-tenant on the board) looks like a hang to a 2 s limit.
-#define F5_WATCHDOG_CYCLES (40000000000ll)
+#ifndef F5_WATCHDOG_NS
+// 25 s of wall time: a stuck pipeline traps instead of hanging the GPU.  It was 2 s of SM cycles until a handful of bench
+// runs (4 of ~50, clustered in time on particular boxes, under ncu too) died with "unspecified launch failure" in otherwise
+// healthy code: the only trap in these kernels is this watchdog, and anything that stops the context for a couple of
+// seconds (profiler pauses, a co-tenant on the board) looks like a hang to a 2 s limit.  The clock is %globaltimer, not
+// clock64: the per-SM cycle counters are not comparable with each other, so a CTA that is preempted and restored on
+// another SM would see an arbitrary jump in clock64 differences.
+#define F5_WATCHDOG_NS (25000000000ll)
 #endif
 
 namespace f5 {
@@ -79,9 +81,10 @@ __device__ __forceinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
         : "memory");
     if (ok) return;
     if ((polls & 4095u) == 0) {
-      const long long now = clock64();
+      long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
       if (t0 == 0) t0 = now;
-      if (now - t0 > F5_WATCHDOG_CYCLES) {
+      if (now - t0 > F5_WATCHDOG_NS) {
 #if F5_WATCHDOG_PRINT
         printf("f5: mbarrier watchdog: grid %d x %d threads, block %d thread %d, barrier at smem %u parity %u\n", gridDim.x,
                blockDim.x, blockIdx.x, threadIdx.x, bar, parity);
