@@ -119,6 +119,13 @@ int f5_cfg_euler(float* x, int64_t ldx, const float* pred, int64_t ldp, int32_t 
                  const int32_t* row_pos, const float* dts, int32_t step, float cfg_strength, void* xb, int64_t ldxb,
                  int32_t C_pad, void* stream);
 
+/* Initial noise y0_i = randn(n_i, C) drawn on the device (model/cfm.py:181-186: `torch.randn(dur, num_channels, device=...)`;
+ * the server passes no seed, so every request is a fresh draw).  Philox4x32-10 keyed by utt_seed[row_utt[row]], counter
+ * (row_pos[row] * 32 + lane, 0x4635, 0, 0), Box-Muller on 24-bit uniforms: the value at (seed, frame, channel) is independent of
+ * the packing.  Rows with row_pos < 0 are zero-filled.  x: fp32 [M, ldx] (columns [C, ldx) untouched), C <= 128. */
+int f5_randn_rows(float* x, int64_t ldx, int32_t M, int32_t C, const int32_t* row_pos, const int32_t* row_utt,
+                  const uint64_t* utt_seed, void* stream);
+
 /* Sinusoidal time embedding (model/modules.py:154-160): out_bf16[s, :] = [sin((1000 t_s) f_k) | cos(...)], k < dim/2;
  * freqs = exp(-k ln(1e4)/(dim/2-1)) is passed in (fp32 [dim/2]). */
 int f5_time_sinus(const float* t, int32_t steps, const float* freqs, int32_t dim, void* out_bf16, int64_t ldo,
@@ -144,6 +151,15 @@ int f5_istft_ola(const float* frames, const float* window, const int32_t* seg, i
  * range of frequency bins where column m of fbank is non-zero; mel: fp32 [rows, ldm], one row per frame. */
 int f5_mel_frames(const float* wave, const int32_t* seg, int32_t num_segs, int32_t max_frames, const float* window,
                   const float* fbank, const int32_t* band, int32_t n_mels, float* mel, int64_t ldm, void* stream);
+
+/* Fault record.  Every mbarrier wait in the tcgen05 kernels carries a watchdog: a pipeline that makes no progress for 4 s of
+ * wall time traps (the launch fails with cudaErrorLaunchFailure) instead of hanging the GPU.  Before trapping, the waiting
+ * thread writes 40 64-bit words into `mapped` — pinned host memory the device can address (e.g. cudaHostAlloc; zero it first) —
+ * which stays readable on the host after the CUDA context has died: [0] claimed flag, [1] magic 0x46355744, [2] gridDim.x |
+ * blockDim.x << 32, [3] blockIdx.x | threadIdx.x << 32, [4] barrier shared-memory address | parity << 32, [5] dynamic smem
+ * bytes | cluster rank << 32, [6] ns waited, [8..40) raw state of the CTA's barrier block.  NULL switches it off.  The
+ * reference has no counterpart (torch raises the CUDA error; core/managers.py:78-80 logs and re-raises). */
+int f5_diag_enable(void* mapped);
 
 /* Library / device info. */
 int f5_device_check(void);      /* 0 if the current device is sm_100 */

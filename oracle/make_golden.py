@@ -118,11 +118,43 @@ def make_full(steps=32):
     print(f"full_c1.npz: mel {mel.shape} wave {wave.shape} in {dt:.1f}s on {torch.get_num_threads()} threads")
 
 
+def make_full_sizes(steps=32, c2_indices=(0, 37)):
+    """Benchmark-size fixtures (round 2): full IndicF5 forward pairs at a C2 length (n = 1384) and the C3 length (n = 3069),
+    and complete NFE-32 utterances of the C2 batch, all through the real reference's own modules in fp32."""
+    cfg, vcfg = W.INDICF5, W.VOCOS_24K
+    sd, vsd = W.make_dit_state_dict(cfg, seed=0), W.make_vocos_state_dict(vcfg, seed=0)
+    cfm = R.build_reference_cfm(sd, cfg, vocab_map())
+    voc = R.build_reference_vocos(vsd, vcfg)
+    out = {}
+    for n in (1384, 3069):
+        x, cond, text = S.forward_inputs(n, cfg.vocab_size)
+        t0 = time.time()
+        with torch.inference_mode():
+            out[f"fwd{n}_cond"] = cfm.transformer(x=x, cond=cond, text=text, time=torch.tensor(0.37), drop_audio_cond=False,
+                                                  drop_text=False)[0].numpy()
+            out[f"fwd{n}_null"] = cfm.transformer(x=x, cond=cond, text=text, time=torch.tensor(0.37), drop_audio_cond=True,
+                                                  drop_text=True)[0].numpy()
+        print(f"forward pair n={n}: {time.time() - t0:.1f}s", flush=True)
+    np.savez_compressed(os.path.join(GOLDEN, "full_fwd.npz"), **out)
+    specs = S.workload("c2")
+    out = {"indices": np.asarray(c2_indices, dtype=np.int64)}
+    for k in c2_indices:
+        t0 = time.time()
+        mel, wave = run_reference_utterance(cfm, voc, specs[k], steps=steps)
+        out[f"utt{k}_mel"], out[f"utt{k}_wave"] = mel[specs[k].meta["ref_len"]:], wave
+        print(f"c2 utterance {k}: n={specs[k].duration} in {time.time() - t0:.1f}s", flush=True)
+    np.savez_compressed(os.path.join(GOLDEN, "full_c2_utts.npz"), **out)
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--full", action="store_true", help="also mint the full-size C1 fixture (~2 min CPU)")
+    ap.add_argument("--sizes", action="store_true", help="only mint the benchmark-size fixtures (C2 / C3 lengths, ~6 min CPU)")
     args = ap.parse_args()
     os.makedirs(GOLDEN, exist_ok=True)
+    if args.sizes:
+        make_full_sizes()
+        sys.exit(0)
     make_tiny()
     if args.full:
         make_full()

@@ -263,3 +263,62 @@ def test_sample_prologue_rules():
     utts = CFM._prepare(stub, cond[:1], ["abz"], 64, None, None, 4096, None, [torch.ones(80, 100)])
     assert utts[0].n == 64 and utts[0].cond_len == 40 and utts[0].text_ids.tolist() == [1, 2, 0]
     assert utts[0].y0.shape == (64, 100) and bool((utts[0].y0 == 1).all())
+
+
+# ------------------------------------------------------------------------------------------------ round 2: noise, loader
+def test_philox_oracle_matches_random123_known_answers():
+    """Pins oracle/philox.py (the checker of the device noise kernel) to the published Random123 philox4x32-10 vectors."""
+    from oracle import philox as P
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0), (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, want in kat:
+        got = P.philox4x32_10(*[[c] for c in ctr], *key)
+        assert tuple(int(g[0]) for g in got) == want
+    z = P.randn_rows(0xDEADBEEFCAFEF00D, 3000)
+    assert z.shape == (3000, 100) and abs(float(z.mean())) < 5e-3 and abs(float(z.std()) - 1.0) < 5e-3
+    assert np.array_equal(P.randn_rows(7, 50)[:20], P.randn_rows(7, 20))          # counter-based: a prefix is a prefix
+    assert not np.array_equal(P.randn_rows(7, 20), P.randn_rows(8, 20))
+
+
+def test_noise_seeds_follow_the_global_generator():
+    from tts_indic_server_f5_b200 import api
+    torch.manual_seed(123)
+    a = [api.fresh_noise_seed() for _ in range(3)]
+    torch.manual_seed(123)
+    assert a == [api.fresh_noise_seed() for _ in range(3)] and len(set(a)) == 3      # repeatable after manual_seed, fresh otherwise
+    s = {api.utterance_seed(a[0], i) for i in range(1000)}
+    assert len(s) == 1000 and all(0 <= x < 2 ** 64 for x in s)
+
+
+def test_checkpoint_roundtrip_with_the_reference_modules_real_keys(tmp_path):
+    """`utils_infer.py:175-218`: an EMA checkpoint written from the REAL reference module's state dict (shim-loaded CFM) as
+    .safetensors and as .pt comes back through `strip_checkpoint` with exactly the keys the reference's own strict
+    `load_state_dict` accepts, and `infer_dit_config` recovers the architecture.  Needs /root/reference (build container)."""
+    from oracle import ref_shims as R
+    if not R.reference_available():
+        pytest.skip("reference tree not present (GPU box)")
+    from safetensors.torch import load_file, save_file
+    cfg = W.tiny_dit_config()
+    vocab = {t: i for i, t in enumerate(T.synthetic_indic_vocab())}
+    cfm = R.build_reference_cfm(W.make_dit_state_dict(cfg, seed=4), cfg, vocab)
+    real = {k: v.clone() for k, v in cfm.state_dict().items()}
+    assert any(k.startswith("mel_spec.") for k in real) or all(k.startswith("transformer.") for k in real)
+    ema = {"ema_model." + k: v.contiguous() for k, v in real.items()}
+    ema_pt = {**ema, "initted": torch.tensor(True), "step": torch.tensor(1200000)}
+    save_file({**ema, "initted": torch.tensor([1]), "step": torch.tensor([1200000])}, str(tmp_path / "model.safetensors"))
+    torch.save({"ema_model_state_dict": ema_pt}, str(tmp_path / "model.pt"))
+    for sd in (W.strip_checkpoint(load_file(str(tmp_path / "model.safetensors"))),
+               W.strip_checkpoint(torch.load(str(tmp_path / "model.pt"), map_location="cpu", weights_only=True))):
+        # what the reference does with the same file (utils_infer.py:195-213) must accept it strictly
+        legacy = ("mel_spec.mel_stft.mel_scale.fb", "mel_spec.mel_stft.spectrogram.window")
+        assert set(sd) == {k for k in real if k not in legacy}
+        missing, unexpected = cfm.load_state_dict(sd, strict=False)
+        assert not unexpected and set(missing) <= set(legacy)
+        assert W.infer_dit_config(sd) == cfg
+        for k in sd:
+            assert torch.equal(sd[k], real[k])
+    # non-EMA branch (:214-217)
+    torch.save({"model_state_dict": real}, str(tmp_path / "plain.pt"))
+    sd = W.strip_checkpoint(torch.load(str(tmp_path / "plain.pt"), map_location="cpu", weights_only=True), use_ema=False)
+    assert set(sd) >= {k for k in real if k.startswith("transformer.")}

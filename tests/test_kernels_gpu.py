@@ -452,3 +452,37 @@ def test_istft_vs_torch():
         S = (mag * (ph.cos() + 1j * ph.sin())).t()[None]
         ref = torch.istft(S, 1024, 256, 1024, window, center=True)[0] * g
         check(f"istft T={T}", wav[o:o + 256 * (T - 1)], ref, rel=2e-5)
+
+
+# ------------------------------------------------------------------------------------------------ round 2: device noise
+def test_randn_rows_vs_philox_oracle():
+    """f5_randn_rows against oracle/philox.py (itself pinned to the Random123 known answers): identical Philox words, so the
+    normals agree to float round-off of log / sincospi (1e-5 abs on values up to ~5); gap rows are zero; the draw of an
+    utterance does not depend on where it sits in the pack."""
+    from oracle import philox as P
+    from tts_indic_server_f5_b200.layout import build_layout
+    lens, seeds = [37, 130, 5], [7, 0xDEADBEEFCAFEF00D, 2 ** 63 + 11]
+    L = build_layout(lens)
+    R = L.half_rows
+    x = torch.full((R, 128), 9.0, device=DEV)
+    sd = torch.tensor([s - (1 << 64) if s >= (1 << 63) else s for s in seeds], dtype=torch.int64, device=DEV)
+    ops.randn_rows(x, 100, L.row_pos[:R].to(DEV), L.row_utt.to(DEV), sd)
+    torch.cuda.synchronize()
+    got = x.cpu().numpy()
+    assert (got[:, 100:] == 9.0).all()                                   # columns past C untouched
+    live = L.row_pos[:R].numpy() >= 0
+    assert (got[~live, :100] == 0.0).all()
+    for s0, n, seed in zip(L.starts, lens, seeds):
+        want = P.randn_rows(seed, n)
+        err = float(abs(got[s0:s0 + n, :100] - want).max())
+        print(f"[randn_rows] n={n} max-abs {err:.2e}")
+        assert err < 2e-5
+    L2 = build_layout([130])                                              # the same utterance alone: bit-identical rows
+    y = torch.zeros(L2.half_rows, 128, device=DEV)
+    ops.randn_rows(y, 100, L2.row_pos[:L2.half_rows].to(DEV), L2.row_utt.to(DEV), sd[1:2].contiguous())
+    assert torch.equal(y[L2.starts[0]:L2.starts[0] + 130, :100], x[L.starts[1]:L.starts[1] + 130, :100])
+    big = torch.zeros(4096 + 128, 128, device=DEV)                         # moments at the longest utterance the path allows
+    Lb = build_layout([4096])
+    ops.randn_rows(big[:Lb.half_rows], 100, Lb.row_pos[:Lb.half_rows].to(DEV), Lb.row_utt.to(DEV), sd[:1].contiguous())
+    z = big[Lb.starts[0]:Lb.starts[0] + 4096, :100]
+    assert abs(float(z.mean())) < 5e-3 and abs(float(z.std()) - 1) < 5e-3 and float(z.abs().max()) < 6.0

@@ -8,7 +8,9 @@ Tolerances (bf16 tensor-core operands; fp32 accumulation, residual stream, Layer
   wave  SNR    >= 40 dB                                    (measured 44.7..50.1 dB)
 For scale: the reference's OWN bf16 mode (whole-module .to(bfloat16)) sits at rel-L2 1.33e-2, L-inf 0.156 from its fp32
 result on the tiny case (tests/golden/ref_bf16_error.json) — the CUDA path must be at least that close, and is ~4x closer.
-There is no separate fp32-operand mode in this round (TF32/3xTF32 GEMM variants are future work)."""
+Benchmark sizes (round 2; goldens minted from the real reference by `python -m oracle.make_golden --sizes`):
+  full IndicF5 forward pair at n = 1384 (C2) and n = 3069 (C3)   rel-L2 <= 1.0e-2 per branch
+  two complete NFE-32 utterances INSIDE the packed C2 batch of 64    same mel / wave tolerances as above."""
 import json
 import os
 
@@ -24,6 +26,11 @@ if torch.cuda.is_available():
     from oracle import f5_oracle as O
     from tts_indic_server_f5_b200 import api, ops, synthetic as S, text as T, weights as W
     from tts_indic_server_f5_b200.engine import UtteranceInput
+
+
+def ref_noise(specs):
+    """The noise the golden vectors were minted with (oracle/make_golden.py): CPU generator, seed 1234 + noise_index."""
+    return [S.initial_noise(4096, s.noise_index) for s in specs]
 
 
 def rel(a, b):
@@ -71,7 +78,7 @@ def test_tiny_end_to_end_vs_reference_golden(tiny_models, golden_dir, wl):
     g = np.load(os.path.join(golden_dir, "tiny.npz"))
     bf16_ref = json.load(open(os.path.join(golden_dir, "ref_bf16_error.json")))["tiny"]
     specs = S.workload(wl)
-    waves, mels = api.Synthesizer(model, voc).generate(specs, return_mel=True)
+    waves, mels = api.Synthesizer(model, voc).generate(specs, return_mel=True, y0=ref_noise(specs))
     for i, (spec, wv, ml) in enumerate(zip(specs, waves, mels)):
         gm = g[f"{wl}_{i}_mel"][spec.meta["ref_len"]:]
         assert ml.shape == gm.T.shape and wv.shape == g[f"{wl}_{i}_wave"].shape
@@ -85,7 +92,7 @@ def test_full_size_c1_vs_reference_golden(full_models, golden_dir):
     model, voc = full_models
     g = np.load(os.path.join(golden_dir, "full_c1.npz"))
     spec = S.workload("c1")
-    waves, mels = api.Synthesizer(model, voc).generate(spec, return_mel=True)
+    waves, mels = api.Synthesizer(model, voc).generate(spec, return_mel=True, y0=ref_noise(spec))
     gm = g["mel"][spec[0].meta["ref_len"]:]
     r, li, s = rel(mels[0].T, gm), float(np.abs(mels[0].T - gm).max()), snr(waves[0], g["wave"])
     print(f"full C1: mel rel-L2 {r:.2e} L-inf {li:.3f} wave SNR {s:.1f} dB")
@@ -163,9 +170,9 @@ def test_prompt_cache_reuses_the_voice(tiny_models):
     cfg, vcfg, sd, vsd, model, voc = tiny_models
     syn = api.Synthesizer(model, voc)
     specs = S.workload("tiny3")
-    a = syn.generate(specs)
+    a = syn.generate(specs, noise_seed=11)
     first = (syn.prompt_cache.hits, syn.prompt_cache.misses)
-    b = syn.generate(specs)
+    b = syn.generate(specs, noise_seed=11)
     assert syn.prompt_cache.hits > first[0] and syn.prompt_cache.misses == first[1]
     for x, y in zip(a, b):
         assert np.array_equal(x, y)                # cached mel == recomputed mel, bit for bit
@@ -179,12 +186,12 @@ def test_request_scheduler_equals_per_request_calls(tiny_models, tmp_path):
     ref_text = T.finish_ref_text(T.synthetic_indic_text(30, 1, "kannada"))
     texts = [T.synthetic_indic_text(60, 2, "kannada"), " ".join(T.synthetic_indic_text(40, 10 + k, "devanagari") + "." for k in range(4))]
     sched = api.RequestScheduler(api.Synthesizer(model, voc), max_rows=6144, max_utts=3, nfe_step=8)
-    ids = [sched.submit((audio, 24000), ref_text, t) for t in texts]
+    ids = [sched.submit((audio, 24000), ref_text, t, seed=100 + k) for k, t in enumerate(texts)]
     assert len(sched.pending[1].chunks) >= 2                                 # the second text does not fit one chunk
     out = sched.run()
     assert sched.pending == [] and len(sched.last_packs) >= 2                # the row budget forced several packs
-    for rid, t in zip(ids, texts):
-        wave, sr, mel = api.infer_process((audio, 24000), ref_text, t, model, voc, nfe_step=8)
+    for k, (rid, t) in enumerate(zip(ids, texts)):
+        wave, sr, mel = api.infer_process((audio, 24000), ref_text, t, model, voc, nfe_step=8, seed=100 + k)
         assert sr == out[rid][1] == 24000
         np.testing.assert_array_equal(out[rid][0], wave)
         np.testing.assert_array_equal(out[rid][2], mel)
@@ -207,15 +214,15 @@ def test_step_graph_is_reused_across_lengths(tiny_models):
 
     a = specs_for([150, 200, 170])
     b = specs_for([155, 195, 170])            # other lengths, same total rows after 128-row padding, same padded item count
-    syn.generate(a)
+    syn.generate(a, noise_seed=3)
     eng = model.engine
     c0, r0 = eng.graph_captures, eng.graph_replays
-    wb = syn.generate(b)
+    wb = syn.generate(b, noise_seed=3)
     assert (eng.graph_captures, eng.graph_replays) == (c0, r0 + 1), "a new length signature must not re-capture the step graph"
     fresh = api.Synthesizer(api.load_model(state_dict=sd), voc)
-    for x, y in zip(wb, fresh.generate(b)):
+    for x, y in zip(wb, fresh.generate(b, noise_seed=3)):
         np.testing.assert_array_equal(x, y)
-    syn.generate(a)                           # and back
+    syn.generate(a, noise_seed=3)             # and back
     assert eng.graph_captures == c0
 
 
@@ -245,8 +252,8 @@ def test_packing_invariance_and_graph_equals_eager_full_size(full_models):
     model, voc = full_models
     syn = api.Synthesizer(model, voc)
     specs = S.workload("small8")
-    waves = syn.generate(specs, nfe_step=4)
-    alone = syn.generate([specs[3]], nfe_step=4)[0]
+    waves = syn.generate(specs, nfe_step=4, noise_seed=9)
+    alone = syn.generate([specs[3]], nfe_step=4, noise_seed=9)[0]   # same Philox key => same noise whatever the packing
     s_pack = snr(waves[3], alone)
     print(f"packed vs alone (through the batched prompt STFT) SNR {s_pack:.1f} dB")
     assert alone.shape == waves[3].shape and s_pack > 90.0   # identical up to the batched-vs-single prompt STFT plan
@@ -264,10 +271,10 @@ def test_packing_invariance_and_graph_equals_eager_full_size(full_models):
     assert torch.equal(outb[2, : int(durs[2])], out2[0])
     model.engine.use_graphs = False
     try:
-        eager = syn.generate(specs, nfe_step=4)
+        eager = syn.generate(specs, nfe_step=4, noise_seed=9)
     finally:
         model.engine.use_graphs = True
-    again = syn.generate(specs, nfe_step=4)
+    again = syn.generate(specs, nfe_step=4, noise_seed=9)
     assert all(np.array_equal(a, b) for a, b in zip(eager, again))
 
 
@@ -290,3 +297,133 @@ def test_infer_process_and_manager_surface(tiny_models, tmp_path):
     assert not mgr.model
     with pytest.raises(ValueError, match="TTS model not loaded"):
         mgr.synthesize("x", p, ref_text)
+
+
+# ------------------------------------------------------------------------------------------------ round 2: benchmark sizes
+@pytest.mark.parametrize("n", [1384, 3069])
+def test_full_size_forward_pair_at_benchmark_lengths(full_models, golden_dir, n):
+    """One CFG velocity pair of the full IndicF5 DiT at a C2 length (1384) and the C3 long-form length (3069: 24 key tiles per
+    query tile, the attention-heavy case) against the real reference's `DiT.forward` (dit.py:130-163) on the same inputs."""
+    model, _ = full_models
+    g = np.load(os.path.join(golden_dir, "full_fwd.npz"))
+    x, cond, text = S.forward_inputs(n, W.INDICF5.vocab_size)
+    u = UtteranceInput(cond=cond[0], text_ids=text[0], n=n, cond_len=n, y0=x[0])
+    pc = model.engine.forward_flow([u], 0.37)[0].cpu().numpy()
+    for k, name in enumerate(("cond", "null")):
+        want = g[f"fwd{n}_{name}"]
+        r, li = rel(pc[k], want), float(np.abs(pc[k] - want).max())
+        print(f"forward n={n} {name}: rel-L2 {r:.2e} L-inf {li:.3f} (|ref| max {np.abs(want).max():.2f})")
+        assert r < MEL_REL
+    # the same utterance inside a ragged pack (three other lengths around it) is bit-identical to the utterance alone
+    others = [UtteranceInput(cond=cond[0, :m], text_ids=text[0, :50], n=m, cond_len=m, y0=x[0, :m]) for m in (200, 731)]
+    packed = model.engine.forward_flow([others[0], u, others[1]], 0.37)[1]
+    assert torch.equal(packed.cpu(), torch.from_numpy(pc))
+
+
+def test_c2_batch_utterances_vs_reference_golden(full_models, golden_dir):
+    """The benchmark workload itself: all 64 utterances of C2 through `Synthesizer.generate` (one packed batch, 32 Euler steps,
+    CFG pair, Vocos), utterances 0 (n = 1384) and 37 (n = 1277) compared with the real reference's `CFM.sample` + Vocos run
+    one utterance at a time in fp32 on the same noise (cfm.py:162-176, utils_infer.py:459-476)."""
+    model, voc = full_models
+    g = np.load(os.path.join(golden_dir, "full_c2_utts.npz"))
+    specs = S.workload("c2")
+    waves, mels = api.Synthesizer(model, voc).generate(specs, return_mel=True, y0=S.reference_noise(specs))
+    for k in g["indices"]:
+        gm, gw = g[f"utt{k}_mel"], g[f"utt{k}_wave"]
+        r, li, s = rel(mels[k].T, gm), float(np.abs(mels[k].T - gm).max()), snr(waves[k], gw)
+        print(f"C2 utterance {k} (n={specs[k].duration}) in the 64-pack: mel rel-L2 {r:.2e} L-inf {li:.3f} wave SNR {s:.1f} dB")
+        assert mels[k].T.shape == gm.shape and waves[k].shape == gw.shape
+        assert r < MEL_REL and li < MEL_LINF and s > WAVE_SNR
+
+
+def test_tts_manager_load_and_synthesize_vs_oracle(tiny_models, tmp_path):
+    """Boundary #1 end to end (managers.py:62-85): `TTSManager().load()` then `.synthesize(text, ref_audio_path, ref_text)` on a
+    WAV file with silent edges -> int16 array, against the oracle chain on the same file: pydub-port prompt conditioning
+    (utils_infer.py:285-320) -> '. ' rule -> byte-budget chunking -> per-chunk `infer_one` (fp32) -> cross-fade -> int16."""
+    import wave as wavmod
+    from oracle import pydub_port as PP
+    cfg, vcfg, sd, vsd, _, _ = tiny_models
+    rate = 24000
+    body = S.prompt_audio(1.2, 3)[0].numpy()
+    pcm = np.concatenate([np.zeros(int(0.25 * rate)), body, np.zeros(int(0.4 * rate))])
+    path = str(tmp_path / "ref.wav")
+    with wavmod.open(path, "wb") as w:
+        w.setnchannels(1); w.setsampwidth(2); w.setframerate(rate)
+        w.writeframes(np.clip(np.round(pcm * 32767), -32768, 32767).astype("<i2").tobytes())
+    ref_text = T.synthetic_indic_text(24, 1)
+    gen = ". ".join(T.synthetic_indic_text(50, 20 + i) for i in range(5)) + "."
+    mgr = api.TTSManager(state_dict=sd, vocoder_state_dict=vsd)
+    mgr.load()
+    assert mgr.model
+    mgr.load()                                                               # idempotent
+    mgr.model.noise_fn = lambda i, n: S.initial_noise(n, i)
+    got = mgr.synthesize(gen, ref_audio_path=path, ref_text=ref_text)
+    assert got.dtype == np.int16 and got.ndim == 1
+    # ---- oracle chain
+    seg = PP.clip_reference(PP.Seg.from_wav(path), True, lambda *_: None)
+    audio = torch.from_numpy(np.frombuffer(seg._data, dtype="<i2").astype(np.float32) / 32768.0)[None]
+    assert audio.shape[-1] < len(pcm) - int(0.5 * rate)                      # the silent edges were trimmed
+    rt = T.finish_ref_text(ref_text)
+    max_chars = int(len(rt.encode("utf-8")) / (audio.shape[-1] / rate) * (25 - audio.shape[-1] / rate))
+    chunks = T.chunk_text(gen, max_chars=max_chars)
+    assert len(chunks) >= 2
+    vocab = {t: i for i, t in enumerate(T.synthetic_indic_vocab())}
+    waves = []
+    with torch.inference_mode():
+        for i, ch in enumerate(chunks):
+            a, _ = O.rms_normalise(audio)
+            ids = O.list_str_to_idx(T.convert_char_to_pinyin([rt + ch]), vocab)
+            dur = O.estimate_duration(a.shape[-1] // 256, rt, ch)
+            wv, _ = O.infer_one(sd, cfg, vsd, vcfg, audio, ids, dur, y0=S.initial_noise(4096, i))
+            waves.append(wv.numpy())
+    want = np.clip(O.cross_fade(waves) * 32768.0, -32768, 32767).astype(np.int16)
+    assert got.shape == want.shape
+    s = snr(got.astype(np.float64), want.astype(np.float64))
+    print(f"TTSManager.synthesize vs oracle chain: {len(chunks)} chunks, {len(got)} samples, SNR {s:.1f} dB")
+    assert s > 38.0                                                          # bf16-operand path + int16 quantisation
+    # default path: a fresh device draw per call (the reference is stochastic unless seeded, cfm.py:181-186)
+    mgr.model.noise_fn = None
+    a1, a2 = mgr.synthesize(gen, path, ref_text), mgr.synthesize(gen, path, ref_text)
+    assert a1.shape == a2.shape == got.shape and not np.array_equal(a1, a2)
+    torch.manual_seed(5)
+    b1 = mgr.synthesize(gen, path, ref_text)
+    torch.manual_seed(5)
+    assert np.array_equal(b1, mgr.synthesize(gen, path, ref_text))           # ... and repeatable under torch.manual_seed
+
+
+def test_checkpoint_file_loads_like_the_state_dict(tiny_models, tmp_path):
+    """`load_model(ckpt_path=...)` on an EMA .safetensors / .pt file (utils_infer.py:195-213 key rules) builds the same engine
+    as the in-memory state dict: bit-identical samples."""
+    from safetensors.torch import save_file
+    cfg, _, sd, _, model, _ = tiny_models
+    ema = {"ema_model." + k: v.contiguous() for k, v in sd.items()}
+    save_file({**ema, "initted": torch.tensor([1]), "step": torch.tensor([7])}, str(tmp_path / "m.safetensors"))
+    torch.save({"ema_model_state_dict": {**ema, "initted": torch.tensor(True), "step": torch.tensor(7)}}, str(tmp_path / "m.pt"))
+    mel = O.mel_spectrogram(S.prompt_audio(0.5, 1)).permute(0, 2, 1)
+    texts = [T.convert_char_to_pinyin([T.synthetic_indic_text(30, 4)])[0]]
+    y0 = [S.initial_noise(100, 0)]
+    want, _ = model.sample(cond=mel, text=texts, duration=90, steps=4, cfg_strength=2.0, sway_sampling_coef=-1.0, y0=y0)
+    for f in ("m.safetensors", "m.pt"):
+        m2 = api.load_model(ckpt_path=str(tmp_path / f))
+        assert m2.cfg == cfg
+        got, _ = m2.sample(cond=mel, text=texts, duration=90, steps=4, cfg_strength=2.0, sway_sampling_coef=-1.0, y0=y0)
+        assert torch.equal(got, want)
+
+
+def test_engine_rejects_what_it_cannot_hold(tiny_models):
+    """Loud failures instead of out-of-range device reads: too many Euler steps for the hoisted tables, a token id beyond the
+    embedding (nn.Embedding raises IndexError at dit.py:56), a re-staged workspace."""
+    cfg, _, sd, _, model, voc = tiny_models
+    mel = O.mel_spectrogram(S.prompt_audio(0.5, 1)).permute(0, 2, 1)
+    texts = [T.convert_char_to_pinyin([T.synthetic_indic_text(30, 4)])[0]]
+    with pytest.raises(ValueError, match="128 Euler steps"):
+        model.sample(cond=mel, text=texts, duration=90, steps=129, cfg_strength=2.0)
+    bad = torch.full((1, 10), cfg.vocab_size + 5, dtype=torch.long)
+    with pytest.raises(IndexError):
+        model.sample(cond=mel, text=bad, duration=90, steps=2, cfg_strength=2.0)
+    syn = api.Synthesizer(model, voc)
+    specs = S.workload("tiny3")
+    st1 = syn.stage(specs, noise_seed=1)
+    syn.stage(specs, noise_seed=2)                                            # same packed size: takes over the workspace
+    with pytest.raises(RuntimeError, match="overwritten"):
+        syn.run(st1)

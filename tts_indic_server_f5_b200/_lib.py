@@ -18,7 +18,7 @@ F5_ACT_NONE, F5_ACT_GELU_TANH, F5_ACT_GELU_ERF, F5_ACT_MISH = 0, 1, 2, 3
 EXPORTS = [
     "f5_gemm_bf16", "f5_attention_d64", "f5_layernorm_mod", "f5_dwconv7_ln", "f5_grn_sumsq", "f5_grn_apply",
     "f5_text_gather_pos", "f5_pack_bf16", "f5_where_rows", "f5_cfg_euler", "f5_time_sinus", "f5_silu_bf16",
-    "f5_istft_frames", "f5_istft_ola", "f5_mel_frames", "f5_device_check", "f5_version",
+    "f5_istft_frames", "f5_istft_ola", "f5_mel_frames", "f5_randn_rows", "f5_diag_enable", "f5_device_check", "f5_version",
 ]
 
 
@@ -65,6 +65,8 @@ def _load() -> C.CDLL:
         "f5_istft_frames": [vp, i64, i32, vp, vp, vp],
         "f5_istft_ola": [vp, vp, vp, i32, i32, vp, vp, vp],
         "f5_mel_frames": [vp, vp, i32, i32, vp, vp, vp, i32, vp, i64, vp],
+        "f5_randn_rows": [vp, i64, i32, i32, vp, vp, vp, vp],
+        "f5_diag_enable": [vp],
         "f5_device_check": [],
     }
     for name, args in sig.items():
@@ -103,3 +105,40 @@ def call(name: str, *args) -> None:
     global launch_count
     launch_count += 1
     check(getattr(lib, name)(*args), name)
+
+
+# ------------------------------------------------------------------------------------------ device fault record
+_diag_buf: torch.Tensor | None = None
+
+
+def enable_diag() -> torch.Tensor:
+    """Register a pinned host buffer the mbarrier watchdog writes its record into before it traps (`f5_diag_enable`).
+    Host memory outlives the CUDA context, so `read_diag()` still works after a launch failure made the context unusable."""
+    global _diag_buf
+    if _diag_buf is None:
+        _diag_buf = torch.zeros(64, dtype=torch.int64).pin_memory()
+        check(lib.f5_diag_enable(_diag_buf.data_ptr()), "f5_diag_enable")
+    return _diag_buf
+
+
+def read_diag() -> dict | None:
+    """Decode the watchdog record (layout: csrc/f5_common.cuh).  None: no kernel of this library trapped on its watchdog, so a
+    launch failure seen by the host was something else (memory fault, Xid)."""
+    if _diag_buf is None:
+        return None
+    w = _diag_buf.numpy().view("uint32")
+    if (int(w[0]) & 0xFFF00000) != 0xF5D00000:
+        return None
+    block_dim, smem_kib = int(w[0]) & 0xFFFFF, (int(w[2]) >> 16) & 0xFFFF
+    kernel = {(384, 128): "attn_d64_kernel"}.get((block_dim, smem_kib))
+    if kernel is None:
+        kernel = f"gemm_tcgen05_kernel ({'8' if block_dim == 384 else '4'} epilogue warps, {smem_kib} KiB smem)"
+    bar = int(w[3]) & 0x7FFFFFFF
+    rec = {"kernel": kernel, "block_dim": block_dim, "grid_dim": int(w[1]) >> 16, "block": int(w[1]) & 0xFFFF,
+           "thread": int(w[2]) & 0xFFF, "warp": (int(w[2]) & 0xFFF) // 32, "cluster_rank": (int(w[2]) >> 12) & 0xF,
+           "dynamic_smem_kib": smem_kib, "barrier_smem_addr": bar, "barrier_slot": (bar & 255) // 8, "parity": int(w[3]) >> 31}
+    q = _diag_buf.numpy().view("uint64")
+    if int(q[2]) != 0:
+        rec["waited_ns"] = int(q[3])
+        rec["barrier_words"] = [hex(int(x)) for x in q[8:40]]
+    return rec

@@ -51,6 +51,20 @@ def _default_device() -> str:
     return "cuda" if torch.cuda.is_available() else "cpu"
 
 
+def fresh_noise_seed() -> int:
+    """A 64-bit key for the device noise draw, taken from torch's global CPU generator: like the reference's unseeded
+    `torch.randn` (cfm.py:186) every call is a new draw, and like it `torch.manual_seed(s)` beforehand makes it repeatable."""
+    return int(torch.empty((), dtype=torch.int64).random_())
+
+
+def utterance_seed(base: int, index: int) -> int:
+    """splitmix64 of (base, index): independent Philox keys for the utterances of one request batch."""
+    z = (base + 0x9E3779B97F4A7C15 * (index + 1)) & 0xFFFFFFFFFFFFFFFF
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & 0xFFFFFFFFFFFFFFFF
+    return z ^ (z >> 31)
+
+
 class CFM:
     """Engine-backed stand-in for the reference `CFM` (inference surface only: `.sample`, `.device`, `.eval`, `.to`)."""
 
@@ -98,17 +112,19 @@ class CFM:
             duration = torch.full((batch,), duration, dtype=torch.long)
         duration = torch.maximum(lens_t + 1, torch.as_tensor(duration).long().cpu()).clamp(max=max_duration)  # :136-137
         utts = []
+        base = fresh_noise_seed() if (y0 is None and seed is None) else 0
         for i in range(batch):
             n = int(duration[i])
+            noise = None
             if y0 is not None:
-                noise = (y0[i] if isinstance(y0, (list, tuple)) else y0[i])[:n].float().cpu()
-            else:                                                    # cfm.py:181-186 (drawn on the CPU generator)
-                if seed is not None:
-                    torch.manual_seed(seed)
+                noise = y0[i][:n].float().cpu()
+            elif seed is not None:                                   # cfm.py:182-186: re-seed, then randn, per item — on the CPU
+                torch.manual_seed(seed)                              # generator, so a seeded call reproduces the reference's CPU draw
                 noise = torch.randn(n, self.num_channels, dtype=torch.float32)
             ids = text[i][text[i] != -1]
             em = None if edit_mask is None else edit_mask[i]
-            utts.append(UtteranceInput(cond=cond[i], text_ids=ids, n=n, cond_len=int(lens_t[i]), y0=noise, edit_mask=em))
+            utts.append(UtteranceInput(cond=cond[i], text_ids=ids, n=n, cond_len=int(lens_t[i]), y0=noise, edit_mask=em,
+                                       noise_seed=utterance_seed(base, i)))       # unseeded: drawn on the device (f5_randn_rows)
         return utts
 
     @torch.inference_mode()
@@ -207,10 +223,16 @@ def load_model(model_cls=None, model_cfg=None, mel_spec_type=mel_spec_type, voca
 
 
 def preprocess_ref_audio_text(ref_audio_orig, ref_text, clip_short=True, show_info=print, device=None):
-    """utils_infer.py:282-351, text half: the sentence-final '. ' rule.  The pydub/ffmpeg silence clipping and the
-    Whisper fallback for an empty ref_text are outside the hot path and rejected loudly."""
+    """utils_infer.py:282-351.  Audio half (:285-320): clip to <= 15 s on silences, trim the silent edges at -42 dBFS, append
+    50 ms of silence, re-export — `prompt_audio.py` restates the pydub semantics on integer PCM without pydub / ffmpeg.  Text
+    half (:343-347): the sentence-final '. ' rule.  The Whisper fallback for an empty ref_text (:138-169, :327-338) is outside
+    the served path (the server always passes a transcript, tts_utils.py:19) and is rejected loudly.  A prompt that is already a
+    tensor pair `(audio, sr)` is passed through untouched (our `infer_process` accepts it directly)."""
     if not ref_text.strip():
         raise NotImplementedError("empty ref_text needs the ASR fallback (utils_infer.py:138-169), not on the served path")
+    if isinstance(ref_audio_orig, (str, os.PathLike)):
+        from .prompt_audio import preprocess_ref_audio
+        ref_audio_orig = preprocess_ref_audio(ref_audio_orig, clip_short=clip_short, show_info=show_info)
     return ref_audio_orig, T.finish_ref_text(ref_text)
 
 
@@ -241,12 +263,14 @@ class _Prepared:
     tokens: list
     duration: int
     noise_index: int
+    noise_seed: int | None = None      # explicit Philox key (request scheduler: per-request seeds inside a shared pack)
 
 
 @dataclass
 class Staged:
     """One request batch resident on the device (output of `Synthesizer.stage`)."""
     ws: object
+    generation: int
     layout: object
     preps: list
     frames: list
@@ -270,6 +294,7 @@ class Synthesizer:
         self.last_h2d_bytes = 0
         self.last_d2h_bytes = 0
         self.prompt_cache = PromptCache()
+        self._host_wav: torch.Tensor | None = None
 
     def _prep(self, spec: UtteranceSpec, speed_, fix_duration_) -> _Prepared:
         audio = spec.audio
@@ -291,14 +316,15 @@ class Synthesizer:
             duration = spec.duration
         else:
             duration = T.estimate_duration(ref_len, ref_text, spec.gen_text, speed_, fix_duration_)
-        return _Prepared(audio, rms, ref_len, tokens, duration, spec.noise_index)
+        return _Prepared(audio, rms, ref_len, tokens, duration, spec.noise_index, spec.meta.get("noise_seed"))
 
     @torch.inference_mode()
     def stage(self, specs: list[UtteranceSpec], nfe_step=nfe_step, sway_sampling_coef=sway_sampling_coef, speed=speed,
-              fix_duration=fix_duration, y0: list | None = None) -> "Staged":
-        """Host side + H2D of one request batch: tokenise, duration rule, prompt RMS, pinned copies of prompt audio /
-        noise / tables, prompt mel on the device.  After this the batch is resident in HBM."""
-        from .synthetic import initial_noise
+              fix_duration=fix_duration, y0: list | None = None, noise_seed: int | None = None) -> "Staged":
+        """Host side + H2D of one request batch: tokenise, duration rule, prompt RMS, pinned copies of prompt audio / tables,
+        prompt mel and initial noise on the device.  After this the batch is resident in HBM.  `y0` (one [>= n_i, 100] tensor
+        per utterance) injects the noise instead (parity tests); `noise_seed` fixes the device draw (default: a fresh one per
+        call, cfm.py:181-186 — the reference is stochastic unless seeded)."""
         model, dev = self.model, self.device
         preps = [self._prep(s, speed, fix_duration) for s in specs]
         mels: list = [None] * len(preps)
@@ -326,13 +352,14 @@ class Synthesizer:
                 for i in idx:
                     mels[i] = m
         ids = T.list_str_to_idx([p.tokens for p in preps], model.vocab_char_map)
-        noise = y0 if y0 is not None else [initial_noise(4096, p.noise_index) for p in preps]
+        base = fresh_noise_seed() if (y0 is None and noise_seed is None) else (noise_seed or 0)
         utts = []
-        for p, m, row, nz in zip(preps, mels, ids, noise):                        # CFM.sample prologue, cfm.py:110-138
+        for i, (p, m, row) in enumerate(zip(preps, mels, ids)):                   # CFM.sample prologue, cfm.py:110-138
             tid = row[row != -1]
             lens_i = max(int(tid.numel()), m.shape[0])
             n = min(max(lens_i + 1, p.duration), 4096)
-            utts.append(UtteranceInput(cond=m, text_ids=tid, n=n, cond_len=lens_i, y0=nz))
+            utts.append(UtteranceInput(cond=m, text_ids=tid, n=n, cond_len=lens_i, y0=None if y0 is None else y0[i],
+                                       noise_seed=p.noise_seed if p.noise_seed is not None else utterance_seed(base, p.noise_index)))
         ws, layout = model.engine.stage(utts, nfe_step, sway_sampling_coef)
         h2d += ws.h2d_bytes
         veng = self.vocoder.engine                                                # vocoder rows = generated frames only
@@ -344,7 +371,7 @@ class Synthesizer:
         gains = torch.tensor([p.rms / target_rms if p.rms < target_rms else 1.0 for p in preps], dtype=torch.float32)
         seg = torch.tensor([[s, T_, o, 0] for s, T_, o in zip(starts, frames, offs)], dtype=torch.int32)
         h2d += (src_rows.numel() + pos.numel() + gains.numel() + seg.numel()) * 4
-        st = Staged(ws, layout, preps, frames, offs, tot, src_rows.to(dev), pos.to(dev), gains.to(dev), seg.to(dev),
+        st = Staged(ws, ws.generation, layout, preps, frames, offs, tot, src_rows.to(dev), pos.to(dev), gains.to(dev), seg.to(dev),
                     nfe_step, h2d)
         self.last_h2d_bytes = h2d
         return st
@@ -352,24 +379,26 @@ class Synthesizer:
     @torch.inference_mode()
     def run(self, st: "Staged", cfg_strength=cfg_strength) -> torch.Tensor:
         """Device-resident hot path: sampler + vocoder on a staged batch -> flat fp32 waveform buffer on the device."""
-        self.model.engine.compute(st.ws, st.nfe_step, cfg_strength)
+        self.model.engine.compute(st.ws, st.nfe_step, cfg_strength, generation=st.generation)
         return self.vocoder.engine.decode_rows(st.ws.x, st.src_rows, st.vpos, st.seg, st.frames, st.total, st.gains)
 
     def generate_device(self, specs: list[UtteranceSpec], nfe_step=nfe_step, cfg_strength=cfg_strength,
                         sway_sampling_coef=sway_sampling_coef, speed=speed, fix_duration=fix_duration,
-                        y0: list | None = None):
-        st = self.stage(specs, nfe_step, sway_sampling_coef, speed, fix_duration, y0)
+                        y0: list | None = None, noise_seed: int | None = None):
+        st = self.stage(specs, nfe_step, sway_sampling_coef, speed, fix_duration, y0, noise_seed)
         wav = self.run(st, cfg_strength)
         return wav, st.offs, st.frames, st.total, st.ws, st.layout, st.preps
 
     @torch.inference_mode()
     def generate(self, specs: list[UtteranceSpec], nfe_step=nfe_step, cfg_strength=cfg_strength,
                  sway_sampling_coef=sway_sampling_coef, speed=speed, fix_duration=fix_duration, y0: list | None = None,
-                 return_mel: bool = False):
+                 return_mel: bool = False, noise_seed: int | None = None):
         """-> list of np.float32 waves (and optionally list of np mel [100, F_gen]); host in, host out."""
         wav, offs, frames, tot, ws, layout, preps = self.generate_device(specs, nfe_step, cfg_strength, sway_sampling_coef,
-                                                                         speed, fix_duration, y0)
-        host = torch.empty(tot, dtype=torch.float32).pin_memory()
+                                                                         speed, fix_duration, y0, noise_seed)
+        if self._host_wav is None or self._host_wav.numel() < tot:                # persistent pinned landing buffer (grown, never
+            self._host_wav = torch.empty(max(tot, 1), dtype=torch.float32).pin_memory()   # re-pinned per request)
+        host = self._host_wav[:tot]
         host.copy_(wav[:tot], non_blocking=True)                                  # D2H (:479)
         mel_out = None
         if return_mel:
@@ -377,13 +406,23 @@ class Synthesizer:
                        for ls, n, p in zip(layout.starts, layout.lengths, preps)]
         torch.cuda.current_stream().synchronize()
         self.last_d2h_bytes = tot * 4
-        waves = [host[o:o + 256 * (T_ - 1)].numpy() for o, T_ in zip(offs, frames)]
+        waves = [host[o:o + 256 * (T_ - 1)].numpy().copy() for o, T_ in zip(offs, frames)]   # caller-owned (the landing buffer is reused)
         return (waves, mel_out) if return_mel else waves
+
+
+def _synthesizer_for(model_obj, vocoder) -> "Synthesizer":
+    """One Synthesizer (prompt cache, pinned landing buffer, workspaces through the model's engine) per (model, vocoder) pair:
+    `infer_process` is called once per request and must not rebuild them each time."""
+    syn = getattr(model_obj, "_synthesizer", None)
+    if syn is None or syn.vocoder is not vocoder:
+        syn = Synthesizer(model_obj, vocoder)
+        model_obj._synthesizer = syn
+    return syn
 
 
 def infer_batch_process(ref_audio, ref_text, gen_text_batches, model_obj, vocoder, mel_spec_type="vocos", progress=None,
                         target_rms=0.1, cross_fade_duration=0.15, nfe_step=32, cfg_strength=2.0, sway_sampling_coef=-1,
-                        speed=1, fix_duration=None, device=None, y0: list | None = None):
+                        speed=1, fix_duration=None, device=None, y0: list | None = None, seed: int | None = None):
     """utils_infer.py:406-524.  The chunks of one text are independent until the cross-fade, so they are sampled as ONE
     packed batch instead of the reference's sequential loop; the returned triple is the reference's."""
     if mel_spec_type != "vocos":
@@ -391,8 +430,8 @@ def infer_batch_process(ref_audio, ref_text, gen_text_batches, model_obj, vocode
     audio, sr = ref_audio
     specs = [UtteranceSpec(audio=audio, ref_text=ref_text, gen_text=g, duration=None, noise_index=i, meta={"sr": sr})
              for i, g in enumerate(gen_text_batches)]
-    waves, mels = Synthesizer(model_obj, vocoder).generate(specs, nfe_step, cfg_strength, sway_sampling_coef, speed,
-                                                           fix_duration, y0=y0, return_mel=True)
+    waves, mels = _synthesizer_for(model_obj, vocoder).generate(specs, nfe_step, cfg_strength, sway_sampling_coef, speed,
+                                                                fix_duration, y0=y0, return_mel=True, noise_seed=seed)
     final_wave = cross_fade(waves, cross_fade_duration, target_sample_rate)                   # :485-519
     return final_wave, target_sample_rate, np.concatenate(mels, axis=1)
 
@@ -400,35 +439,64 @@ def infer_batch_process(ref_audio, ref_text, gen_text_batches, model_obj, vocode
 def infer_process(ref_audio, ref_text, gen_text, model_obj, vocoder, mel_spec_type=mel_spec_type, show_info=print,
                   progress=None, target_rms=target_rms, cross_fade_duration=cross_fade_duration, nfe_step=nfe_step,
                   cfg_strength=cfg_strength, sway_sampling_coef=sway_sampling_coef, speed=speed, fix_duration=fix_duration,
-                  device=None):
-    """utils_infer.py:357-400: chunk the text by the byte budget, then `infer_batch_process`."""
+                  device=None, y0: list | None = None, seed: int | None = None):
+    """utils_infer.py:357-400: chunk the text by the byte budget, then `infer_batch_process`.  The noise is a fresh device draw
+    per call like the reference's (cfm.py:186); `seed` fixes it, `y0` (one tensor per text chunk) injects it (parity tests)."""
     audio, sr = _load_audio(ref_audio) if isinstance(ref_audio, (str, os.PathLike)) else ref_audio
     max_chars = int(len(ref_text.encode("utf-8")) / (audio.shape[-1] / sr) * (25 - audio.shape[-1] / sr))
     gen_text_batches = T.chunk_text(gen_text, max_chars=max_chars)
     return infer_batch_process((audio, sr), ref_text, gen_text_batches, model_obj, vocoder, mel_spec_type=mel_spec_type,
                                target_rms=target_rms, cross_fade_duration=cross_fade_duration, nfe_step=nfe_step,
                                cfg_strength=cfg_strength, sway_sampling_coef=sway_sampling_coef, speed=speed,
-                               fix_duration=fix_duration, device=device)
+                               fix_duration=fix_duration, device=device, y0=y0, seed=seed)
 
 
 class INF5Model:
     """Stand-in for the HF remote-code `ai4bharat/IndicF5` model object the server calls
-    (`self.model(text, ref_audio_path=..., ref_text=...)`, managers.py:82-85): returns a 1-D 24 kHz numpy array."""
+    (`self.model(text, ref_audio_path=..., ref_text=...)`, managers.py:82-85): returns a 1-D 24 kHz numpy array.
+    The conditioned prompt (utils_infer.py:285-320) is cached per voice, keyed by the md5 of the prompt file's bytes like the
+    reference's own `_ref_audio_cache` (:322-325): the server re-downloads the same prompt for every request
+    (tts_utils.py:31-36,54-58)."""
 
     def __init__(self, vocab_file: str = "", device: str | None = None, ckpt_path: str | None = None,
-                 vocoder_path: str = "", seed: int = 0, output_int16: bool = True):
+                 vocoder_path: str = "", seed: int = 0, output_int16: bool = True, model_cfg: dict | None = None,
+                 state_dict: dict | None = None, vocoder_state_dict: dict | None = None):
         device = device or _default_device()
-        self.vocoder = load_vocoder("vocos", is_local=bool(vocoder_path), local_path=vocoder_path, device=device, seed=seed)
-        self.ema_model = load_model(None, dict(dim=1024, depth=22, heads=16, ff_mult=2, text_dim=512, conv_layers=4),
-                                    vocab_file=vocab_file, device=device, ckpt_path=ckpt_path, seed=seed)
+        self.vocoder = load_vocoder("vocos", is_local=bool(vocoder_path), local_path=vocoder_path, device=device, seed=seed,
+                                    state_dict=vocoder_state_dict)
+        self.ema_model = load_model(None, model_cfg or dict(dim=1024, depth=22, heads=16, ff_mult=2, text_dim=512, conv_layers=4),
+                                    vocab_file=vocab_file, device=device, ckpt_path=ckpt_path, seed=seed, state_dict=state_dict)
         self.output_int16 = output_int16
+        self.noise_fn = None          # tests: callable (chunk index, frames) -> [frames, 100] noise; None: fresh device draw
+        self._prompts: dict[str, tuple] = {}
 
     def to(self, device):
         return self
 
+    def _prompt(self, ref_audio_path, ref_text):
+        import hashlib
+        with open(ref_audio_path, "rb") as f:
+            key = hashlib.md5(f.read()).hexdigest() + "|" + ref_text
+        hit = self._prompts.get(key)
+        if hit is None:
+            path, text = preprocess_ref_audio_text(ref_audio_path, ref_text, show_info=lambda *_: None)
+            audio, sr = _load_audio(path)
+            if path != os.fspath(ref_audio_path):
+                os.unlink(path)                                   # the reference leaks its temp file (delete=False, :284)
+            hit = ((audio, sr), text)
+            if len(self._prompts) >= 64:
+                self._prompts.pop(next(iter(self._prompts)))
+            self._prompts[key] = hit
+        return hit
+
     def __call__(self, text: str, ref_audio_path: str, ref_text: str):
-        ref_audio, ref_text = preprocess_ref_audio_text(ref_audio_path, ref_text)
-        wave, sr, _ = infer_process(ref_audio, ref_text, text, self.ema_model, self.vocoder)
+        ref_audio, ref_text = self._prompt(ref_audio_path, ref_text)
+        y0 = None
+        if self.noise_fn is not None:
+            audio, sr = ref_audio
+            max_chars = int(len(ref_text.encode("utf-8")) / (audio.shape[-1] / sr) * (25 - audio.shape[-1] / sr))
+            y0 = [self.noise_fn(i, 4096) for i in range(len(T.chunk_text(text, max_chars=max_chars)))]
+        wave, sr, _ = infer_process(ref_audio, ref_text, text, self.ema_model, self.vocoder, y0=y0)
         if self.output_int16:
             return np.clip(wave * 32768.0, -32768, 32767).astype(np.int16)
         return wave.astype(np.float32)
@@ -436,18 +504,26 @@ class INF5Model:
 
 class TTSManager:
     """`src/server/core/managers.py:62-85`, byte-compatible surface: `.model` truthiness is the readiness probe
-    (routes/speech.py:24), `load()` is idempotent and re-raises, `synthesize` raises ValueError when unloaded."""
+    (routes/speech.py:24), `load()` is idempotent and re-raises, `synthesize` raises ValueError when unloaded.
+    One addition: a CUDA error is sticky for the process, so after one the manager drops the model (the readiness probe turns
+    503 instead of every later request failing with a 500), keeps the kernel watchdog's record in `failed_reason`, and
+    refuses to reload inside the dead context."""
 
     def __init__(self, device_type=None, **model_kwargs):
         self.device_type = device_type or _default_device()
         self.model = None
         self.repo_id = "ai4bharat/IndicF5"
         self._model_kwargs = model_kwargs
+        self.failed_reason: str | None = None
 
     def load(self):
+        if self.failed_reason is not None:
+            raise RuntimeError(f"TTS engine lost its CUDA context ({self.failed_reason}); restart the process")
         if not self.model:
             logger.info("Loading TTS model IndicF5...")
             try:
+                from . import _lib
+                _lib.enable_diag()
                 self.model = INF5Model(device=self.device_type, **self._model_kwargs)
                 self.model = self.model.to(self.device_type)
                 logger.info("TTS model IndicF5 loaded")
@@ -458,7 +534,15 @@ class TTSManager:
     def synthesize(self, text, ref_audio_path, ref_text):
         if not self.model:
             raise ValueError("TTS model not loaded")
-        return self.model(text, ref_audio_path=ref_audio_path, ref_text=ref_text)
+        try:
+            return self.model(text, ref_audio_path=ref_audio_path, ref_text=ref_text)
+        except RuntimeError as e:
+            if "CUDA error" in str(e) or "cudaError" in str(e):
+                from . import _lib
+                self.failed_reason = f"{str(e).splitlines()[0]}; watchdog record: {_lib.read_diag()}"
+                logger.error(f"TTS engine failed: {self.failed_reason}")
+                self.model = None
+            raise
 
 
 def wav_response_bytes(audio: np.ndarray, sample_rate: int = target_sample_rate) -> "io.BytesIO":

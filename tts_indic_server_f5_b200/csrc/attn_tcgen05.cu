@@ -191,7 +191,7 @@ attn_d64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnParams p
       int v_col = 0, v_row = 0;
       auto load_v = [&](uint32_t sv_step) {
         const uint32_t sv = sv_step % ATT_KV_STAGES, pv = (sv_step / ATT_KV_STAGES) & 1;
-        mbar_wait(&v_empty[sv], pv ^ 1);
+        mbar_wait_warp(&v_empty[sv], pv ^ 1, leader);
         if (leader) {
           mbar_expect_tx(&v_full[sv], ATT_TILE_BYTES);
           tma_load_2d(sV + sv * ATT_TILE_BYTES, &tmap_qkv, &v_full[sv], v_col, v_row);
@@ -200,7 +200,7 @@ attn_d64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnParams p
       };
       for (StepWalker c(p); c.valid(); c.next(), ++s) {
         if (c.j == 0) {
-          mbar_wait(&q_empty[0], (item_a & 1) ^ 1);            // previous item's last QK_A has retired
+          mbar_wait_warp(&q_empty[0], (item_a & 1) ^ 1, leader);            // previous item's last QK_A has retired
           if (leader) {
             mbar_expect_tx(&q_full[0], ATT_TILE_BYTES);
             tma_load_2d(sQ, &tmap_qkv, &q_full[0], p.q_col + c.head * ATT_D, c.it.x);
@@ -209,7 +209,7 @@ attn_d64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnParams p
           ++item_a;
         }
         const uint32_t st = s % ATT_KV_STAGES, ph = (s / ATT_KV_STAGES) & 1;
-        mbar_wait(&k_empty[st], ph ^ 1);
+        mbar_wait_warp(&k_empty[st], ph ^ 1, leader);
         if (leader) {
           mbar_expect_tx(&k_full[st], ATT_TILE_BYTES);
           tma_load_2d(sK + st * ATT_TILE_BYTES, &tmap_qkv, &k_full[st], p.k_col + c.head * ATT_D, c.it.y + c.j * ATT_BN);
@@ -217,7 +217,7 @@ attn_d64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnParams p
         __syncwarp();
         if (lane == 0) { F5_TRACE(0, s); }
         if (c.j == 0 && c.ngroups == 2) {
-          mbar_wait(&q_empty[1], (item_b & 1) ^ 1);            // group B's previous item's last QK_B has retired
+          mbar_wait_warp(&q_empty[1], (item_b & 1) ^ 1, leader);            // group B's previous item's last QK_B has retired
           if (leader) {
             mbar_expect_tx(&q_full[1], ATT_TILE_BYTES);
             tma_load_2d(sQ + ATT_TILE_BYTES, &tmap_qkv, &q_full[1], p.q_col + c.head * ATT_D, c.it.x + ATT_BM);
@@ -249,9 +249,9 @@ attn_d64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnParams p
     // S_g(step) = Q_g K^T: waits for the group's previous S to be in registers, then 4 MMAs + commit
     auto issue_qk = [&](int g, const StepWalker& c, uint32_t step, uint32_t& iq, uint32_t& tq) {
       const uint32_t st = step % ATT_KV_STAGES;
-      if (c.j == 0) { mbar_wait(&q_full[g], iq & 1); ++iq; }
-      mbar_wait(&k_full[st], (step / ATT_KV_STAGES) & 1);
-      if (tq > 0) mbar_wait(&s_free[g], (tq - 1) & 1);
+      if (c.j == 0) { mbar_wait_warp(&q_full[g], iq & 1, leader); ++iq; }
+      mbar_wait_warp(&k_full[st], (step / ATT_KV_STAGES) & 1, leader);
+      if (tq > 0) mbar_wait_warp(&s_free[g], (tq - 1) & 1, leader);
       tc_fence_after();
       const uint64_t qd = qd0 + g * TILE16, kd = kd0 + st * TILE16;
       if (leader) {
@@ -267,8 +267,8 @@ attn_d64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnParams p
     // O_g (+)= P_g V: P_g from TMEM (8 columns = 16 bf16 keys per MMA), V tile rows kk*16.. (2 KB per MMA)
     auto issue_pv = [&](int g, const StepWalker& c, uint32_t step, uint32_t& tp) {
       const uint32_t st = step % ATT_KV_STAGES;
-      mbar_wait(&v_full[st], (step / ATT_KV_STAGES) & 1);
-      mbar_wait(&p_full[g], tp & 1);                // group g wrote P_g (and read out the previous item's O_g if j == 0)
+      mbar_wait_warp(&v_full[st], (step / ATT_KV_STAGES) & 1, leader);
+      mbar_wait_warp(&p_full[g], tp & 1, leader);                // group g wrote P_g (and read out the previous item's O_g if j == 0)
       tc_fence_after();
       const uint64_t vd = vd0 + st * TILE16;
       const bool first = c.j == 0;
@@ -288,8 +288,16 @@ attn_d64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnParams p
     while (cur.valid()) {
       if (lane == 0) { F5_TRACE(1, ev); }
       ++ev;
+#if F5_WAIT_ALL_LANES
       if (nxt.valid()) issue_qk(0, nxt, a + 1, iq0, tq0);          // QK_A(a+1): at the start of softmax_A(a)
       mbar_wait(a_gate, a & 1);                                    // softmax_A(a) is past its row max
+#else
+      // The gate is waited for BEFORE QK_A(a+1) is issued (round 1 had it after): group A reaches gate(a+1) only through
+      // S_A(a+1), so with this order a_gate can never complete a second phase while this warp still waits for the first.
+      // It costs QK_A(a+1) one row-max pass (~200 cycles) of head start out of the ~2000 it has before softmax_A(a) ends.
+      mbar_wait_warp(a_gate, a & 1, leader);                       // softmax_A(a) is past its row max
+      if (nxt.valid()) issue_qk(0, nxt, a + 1, iq0, tq0);          // QK_A(a+1): during softmax_A(a)
+#endif
       if (cur.ngroups == 2) issue_qk(1, cur, a, iq1, tq1);         // QK_B(a): group B runs half a tile behind A
       if (leader) umma_commit(&k_empty[a % ATT_KV_STAGES]);        // QK_A(a) (issued a step ago) and QK_B(a) retired -> K stage reusable
       __syncwarp();
@@ -493,6 +501,8 @@ static long long* g_trace_buf = nullptr;
 
 }  // namespace f5
 
+F5_DEFINE_DIAG_SETTER(f5_diag_set_attn)
+
 extern "C" int f5_attention_trace_dump(long long* host) {
   if (f5::g_trace_buf == nullptr) return F5_ERR_ARG;
   cudaDeviceSynchronize();
@@ -509,12 +519,9 @@ extern "C" int f5_attention_d64(const void* qkv, int64_t ld, int32_t rows, int32
   CUtensorMap tq;
   int rc = make_tmap_bf16_2d(&tq, qkv, rows, cols, ld, 128);
   if (rc != F5_OK) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attn_d64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM);
-    if (e != cudaSuccess) return static_cast<int>(e);
-    attr_set = true;
-  }
+  static const cudaError_t attr_rc =       // C++11 magic static: set once, thread-safe
+      cudaFuncSetAttribute(attn_d64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM);
+  if (attr_rc != cudaSuccess) return static_cast<int>(attr_rc);
   AttnParams p;
   p.q_col = q_col; p.k_col = k_col; p.v_col = v_col; p.heads = heads;
   p.items = items;
@@ -522,13 +529,13 @@ extern "C" int f5_attention_d64(const void* qkv, int64_t ld, int32_t rows, int32
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
   p.ldo = ldo;
   p.scale_log2 = softmax_scale * 1.4426950408889634f;
-  static long long* trace_buf = nullptr;
-  if (getenv("F5_ATTN_TRACE") != nullptr && trace_buf == nullptr) {
-    cudaMalloc(&trace_buf, 4 * 512 * sizeof(long long));
-    cudaMemset(trace_buf, 0, 4 * 512 * sizeof(long long));
+#if ATT_TRACE
+  if (g_trace_buf == nullptr) {          // trace builds only (tools/attn_trace.py): the product launcher never allocates
+    cudaMalloc(&g_trace_buf, 4 * 512 * sizeof(long long));
+    cudaMemset(g_trace_buf, 0, 4 * 512 * sizeof(long long));
   }
-  p.trace = trace_buf;
-  g_trace_buf = trace_buf;
+#endif
+  p.trace = g_trace_buf;
   const int grid = p.num_work < kNumSMsB200 ? p.num_work : kNumSMsB200;
   attn_d64_kernel<<<grid, ATT_THREADS, ATT_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(tq, p);
   return static_cast<int>(cudaGetLastError());

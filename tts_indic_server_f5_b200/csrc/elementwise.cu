@@ -268,6 +268,55 @@ __global__ void __launch_bounds__(256) cfg_euler_kernel(float* __restrict__ x, l
   }
 }
 
+// ------------------------------------------------------------------------------------------------ initial noise
+// y0 = randn(n_i, C) per utterance (reference model/cfm.py:181-186 draws it with torch.randn on the model's device).  Counter-
+// based so that the value at (utterance seed, frame, channel) does not depend on how the batch is packed: Philox4x32-10 keyed
+// by the utterance's 64-bit seed, counter = (frame * 32 + lane, 0x4635, 0, 0); each draw gives four 32-bit words = two Box-
+// Muller pairs = channels 4*lane .. 4*lane+3.  One warp per row; gap rows (row_pos < 0) are zero-filled.
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                                              uint32_t (&out)[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    c0 = hi1 ^ c1 ^ k0; c1 = lo1; c2 = hi0 ^ c3 ^ k1; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+__device__ __forceinline__ float2 box_muller(uint32_t a, uint32_t b) {
+  const float u1 = (static_cast<float>(a >> 8) + 1.0f) * 5.9604644775390625e-8f;   // (0, 1]
+  const float u2 = static_cast<float>(b >> 8) * 5.9604644775390625e-8f;            // [0, 1)
+  const float r = sqrtf(-2.0f * logf(u1));
+  float sn, cs;
+  sincospif(2.0f * u2, &sn, &cs);
+  return make_float2(r * cs, r * sn);
+}
+__global__ void __launch_bounds__(256) randn_rows_kernel(float* __restrict__ x, long long ldx, int M, int C,
+                                                         const int* __restrict__ row_pos, const int* __restrict__ row_utt,
+                                                         const unsigned long long* __restrict__ utt_seed) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const int lane = threadIdx.x & 31;
+  const int pos = row_pos[row];
+  float* xr = x + static_cast<size_t>(row) * ldx;
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (pos >= 0 && 4 * lane < C) {
+    const unsigned long long seed = utt_seed[row_utt[row]];
+    uint32_t w[4];
+    philox4x32_10(static_cast<uint32_t>(pos) * 32u + lane, 0x4635u, 0u, 0u, static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32), w);
+    const float2 a = box_muller(w[0], w[1]), b = box_muller(w[2], w[3]);
+    v = make_float4(a.x, a.y, b.x, b.y);
+  }
+  if (4 * lane + 3 < C) {
+    *reinterpret_cast<float4*>(xr + 4 * lane) = v;
+  } else {
+    const float e[4] = {v.x, v.y, v.z, v.w};
+    for (int i = 0; i < 4; ++i)
+      if (4 * lane + i < C) xr[4 * lane + i] = e[i];
+  }
+}
+
 __global__ void time_sinus_kernel(const float* __restrict__ t, int steps, const float* __restrict__ freqs, int dim,
                                   __nv_bfloat16* __restrict__ out, long long ldo) {
   const int s = blockIdx.x;
@@ -376,6 +425,14 @@ extern "C" int f5_cfg_euler(float* x, int64_t ldx, const float* pred, int64_t ld
   return F5_LAUNCH_RC();
 }
 
+extern "C" int f5_randn_rows(float* x, int64_t ldx, int32_t M, int32_t C, const int32_t* row_pos, const int32_t* row_utt,
+                             const uint64_t* utt_seed, void* stream) {
+  if (!x || !row_pos || !row_utt || !utt_seed || M <= 0 || C <= 0 || C > 128 || ldx % 4 != 0) return F5_ERR_ARG;
+  randn_rows_kernel<<<(M + 7) / 8, 256, 0, F5_STREAM(stream)>>>(x, ldx, M, C, row_pos, row_utt,
+                                                                reinterpret_cast<const unsigned long long*>(utt_seed));
+  return F5_LAUNCH_RC();
+}
+
 extern "C" int f5_time_sinus(const float* t, int32_t steps, const float* freqs, int32_t dim, void* out, int64_t ldo,
                              void* stream) {
   if (!t || !freqs || !out || steps <= 0 || dim <= 0 || dim % 2 != 0) return F5_ERR_ARG;
@@ -399,4 +456,4 @@ extern "C" int f5_device_check(void) {
   return (prop.major == 10 && prop.minor == 0) ? F5_OK : F5_ERR_ARCH;
 }
 
-extern "C" const char* f5_version(void) { return "f5_b200 0.1 (sm_100a; tcgen05/TMEM/TMA)"; }
+extern "C" const char* f5_version(void) { return "f5_b200 0.2 (sm_100a; tcgen05/TMEM/TMA)"; }

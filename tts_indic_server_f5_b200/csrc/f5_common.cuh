@@ -8,13 +8,16 @@
 #include <cstdio>
 
 #ifndef F5_WATCHDOG_NS
-// 25 s of wall time: a stuck pipeline traps instead of hanging the GPU.  It was 2 s of SM cycles until a handful of bench
-// runs (4 of ~50, clustered in time on particular boxes, under ncu too) died with "unspecified launch failure" in otherwise
-// healthy code: the only trap in these kernels is this watchdog, and anything that stops the context for a couple of
-// seconds (profiler pauses, a co-tenant on the board) looks like a hang to a 2 s limit.  The clock is %globaltimer, not
-// clock64: the per-SM cycle counters are not comparable with each other, so a CTA that is preempted and restored on
-// another SM would see an arbitrary jump in clock64 differences.
-#define F5_WATCHDOG_NS (25000000000ll)
+// A stuck pipeline traps instead of hanging the GPU: 4 s of wall time (%globaltimer — per-SM clock64 counters are not
+// comparable across SMs).  Before it traps, the waiting thread leaves a record in host-mapped memory (f5_diag_enable) that
+// names the kernel shape, the CTA / thread, the barrier and the raw state of every barrier of the CTA, so that the host can
+// tell a watchdog trap from a memory fault after the context has died (`_lib.read_diag`).
+#define F5_WATCHDOG_NS (4000000000ll)
+#endif
+// F5_WAIT_ALL_LANES=1 restores the round-1 form of the warp-uniform issue loops, where all 32 lanes of a producer / MMA warp
+// poll the mbarrier themselves (A/B builds for the soak test only; see mbar_wait_warp below).
+#ifndef F5_WAIT_ALL_LANES
+#define F5_WAIT_ALL_LANES 0
 #endif
 
 namespace f5 {
@@ -34,6 +37,55 @@ __device__ __forceinline__ bool elect_one() {
       "selp.u32 %0, 1, 0, P;\n\t}\n"
       : "=r"(pred));
   return pred != 0;
+}
+
+// ------------------------------------------------------------------ device-side fault record
+// One pointer per translation unit (no -rdc): set by f5_diag_enable() through the F5_DEFINE_DIAG_SETTER each .cu defines.
+// The record is ONE 16-byte store (any timed-out thread's record is a valid one; they are all stuck on the same pipeline):
+//   u32[0] = 0xF5D00000 | blockDim.x          u32[1] = blockIdx.x | gridDim.x << 16
+//   u32[2] = threadIdx.x | cluster cta rank << 12 | dynamic smem KiB << 16     u32[3] = barrier smem address | parity << 31
+// It is inlined at every wait (a call inside a setmaxnreg region does not register-allocate), so it is kept to a dozen
+// instructions: the attention kernel is sensitive to its instruction footprint.  -DF5_DIAG_FULL=1 (soak builds) appends
+// u64[2] = claim flag, u64[3] = ns waited, u64[8..40) = the 32 eight-byte words at (barrier & ~255): the raw state of every
+// mbarrier of the CTA (each kernel keeps its barriers inside one 256-byte aligned block).
+#ifndef F5_DIAG_FULL
+#define F5_DIAG_FULL 0
+#endif
+#ifndef F5_DIAG
+#define F5_DIAG 1             // 0: trap without a record (A/B builds that measure what the record costs)
+#endif
+static __device__ unsigned long long* f5_diag_ptr = nullptr;
+#define F5_DEFINE_DIAG_SETTER(name)                                                                           \
+  int name(void* mapped) {                                                                                    \
+    unsigned long long* p = reinterpret_cast<unsigned long long*>(mapped);                                    \
+    return static_cast<int>(cudaMemcpyToSymbol(f5::f5_diag_ptr, &p, sizeof(p), 0, cudaMemcpyHostToDevice));   \
+  }
+__device__ __forceinline__ void diag_report_and_trap(uint32_t bar, uint32_t parity, long long waited_ns) {
+#if F5_DIAG
+  unsigned long long* d = f5_diag_ptr;
+  if (d != nullptr) {
+    uint32_t dyn, rank;
+    asm volatile("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn));
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    const uint4 rec = make_uint4(0xF5D00000u | blockDim.x, blockIdx.x | (gridDim.x << 16),
+                                 threadIdx.x | (rank << 12) | ((dyn >> 10) << 16), bar | (parity << 31));
+    asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(d), "r"(rec.x), "r"(rec.y), "r"(rec.z), "r"(rec.w) : "memory");
+#if F5_DIAG_FULL
+    if (atomicCAS(d + 2, 0ull, 1ull) == 0ull) {
+      d[3] = static_cast<unsigned long long>(waited_ns);
+      const uint32_t base = bar & ~255u;
+#pragma unroll 1
+      for (int i = 0; i < 32; ++i) {
+        unsigned long long w;
+        asm volatile("ld.shared.b64 %0, [%1];" : "=l"(w) : "r"(base + 8u * i));
+        d[8 + i] = w;
+      }
+    }
+#endif
+    __threadfence_system();
+  }
+#endif
+  __trap();
 }
 
 // ------------------------------------------------------------------ mbarrier
@@ -61,13 +113,9 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 // try_wait suspends the thread in hardware for a bounded time, so the loop is not a hot spin; the watchdog clock is only
-// read every 4096 polls to keep the polling warps (one lane each) off the issue slots the math warps need.  A stuck
-// pipeline traps instead of hanging the GPU; build with -DF5_WATCHDOG_PRINT=1 to also print which barrier it was (the
-// printf call inlined at every wait bloats the attention kernel past the instruction cache and costs registers, and an
-// out-of-line slow path makes ptxas spill the softmax's 128-register score row around the call).
-#ifndef F5_WATCHDOG_PRINT
-#define F5_WATCHDOG_PRINT 0
-#endif
+// read every 4096 polls to keep the polling warps (one lane each) off the issue slots the math warps need.  The report is an
+// out-of-line call on the cold path only (an inlined printf at every wait bloated the attention kernel past the instruction
+// cache; the call sits behind a branch that is never taken in a healthy run).
 __device__ __forceinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
   long long t0 = 0;
   for (uint32_t polls = 1;; ++polls) {
@@ -84,19 +132,28 @@ __device__ __forceinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
       long long now;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
       if (t0 == 0) t0 = now;
-      if (now - t0 > F5_WATCHDOG_NS) {
-#if F5_WATCHDOG_PRINT
-        printf("f5: mbarrier watchdog: grid %d x %d threads, block %d thread %d, barrier at smem %u parity %u\n", gridDim.x,
-               blockDim.x, blockIdx.x, threadIdx.x, bar, parity);
-#endif
-        __trap();
-      }
+      if (now - t0 > F5_WATCHDOG_NS) diag_report_and_trap(bar, parity, now - t0);
     }
   }
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   mbar_wait_slow(smem_u32(bar), parity);
+}
+// Wait of a whole producer / MMA warp that walks its loop warp-uniformly with ONE elected lane issuing (TMA, tcgen05.mma,
+// commits).  Only that lane polls the barrier; the others park at the __syncwarp.  If every lane polled for itself (the
+// round-1 form), a lane that is still inside try_wait when the leader has already moved on is exposed to the phases the
+// leader's own next instruction sets in motion: the leader's TMA lands / its MMAs retire and flip the same barrier AGAIN
+// within ~1 us, the late lane then sees the parity it is waiting for as "not yet complete", and the warp is stuck at the next
+// __syncwarp for good — a parity wait must never be able to fall two phases behind, and with 32 independent pollers nothing
+// in the protocol guaranteed that.  With one poller the thread that observes the phase is the thread that advances it.
+__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, bool leader) {
+#if F5_WAIT_ALL_LANES
+  mbar_wait(bar, parity);
+#else
+  if (leader) mbar_wait(bar, parity);
+  __syncwarp();
+#endif
 }
 // Variants on a 32-bit shared-window address computed ONCE by the caller (the generic-pointer forms re-derive the window
 // base from special registers at every call: S2R + LEA on the critical path of each barrier operation).

@@ -139,7 +139,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         const int n0 = (tile % p.num_n_tiles) * BLOCK_N;
         int tap = 0, kc = 0;
         for (int k = 0; k < p.num_k; ++k) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_wait_warp(&empty_bar[stage], phase ^ 1, leader);
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + Cfg::A_BYTES;
           if (leader) {
@@ -157,6 +157,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
       }
+#if !F5_WAIT_ALL_LANES
+      if (CL > 1) {
+        // Producer tail: the last STAGES stage releases are multicast tcgen05.commit arrivals from BOTH CTAs of the pair, and
+        // nobody waits for them any more.  barrier.cluster orders the executing threads' own operations, not an asynchronous
+        // arrive that is still travelling to the peer's shared memory, so drain every stage's final phase before this CTA
+        // may reach the cluster barrier and exit (the exited CTA's shared memory may already belong to the next kernel).
+        for (int i = 0; i < Cfg::STAGES; ++i) {
+          mbar_wait_warp(&empty_bar[stage], phase ^ 1, leader);
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+#endif
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer (warp-uniform, see the producer)
@@ -169,11 +181,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int tile = first_unit; tile < num_tiles; tile += num_walkers) {
-        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        mbar_wait_warp(&tmem_empty[acc], acc_phase ^ 1, leader);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
         for (int k = 0; k < p.num_k; ++k) {
-          mbar_wait(&full_bar[stage], phase);
+          mbar_wait_warp(&full_bar[stage], phase, leader);
           tc_fence_after();
           const uint64_t adesc = desc0 + static_cast<uint64_t>(stage) * (Cfg::STAGE_BYTES >> 4);   // address field is in 16-B units
           const uint64_t bdesc = adesc + (Cfg::A_BYTES >> 4);
@@ -508,13 +520,9 @@ int launch_gemm(const f5_gemm_args& a, const GemmParams& p, cudaStream_t stream)
   } else {
     tr = ta;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BLOCK_N, ACT, CL, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         Cfg::SMEM_BYTES);
-    if (e != cudaSuccess) return static_cast<int>(e);
-    attr_set = true;
-  }
+  static const cudaError_t attr_rc =       // C++11 magic static (one per template instantiation): set once, thread-safe
+      cudaFuncSetAttribute(gemm_tcgen05_kernel<BLOCK_N, ACT, CL, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+  if (attr_rc != cudaSuccess) return static_cast<int>(attr_rc);
   const int sms = a.num_sms > 0 ? a.num_sms : kNumSMsB200;
   const int units = ((p.num_m_tiles + CL - 1) / CL) * p.num_n_tiles;
   cudaLaunchConfig_t cfg = {};
@@ -530,13 +538,13 @@ int launch_gemm(const f5_gemm_args& a, const GemmParams& p, cudaStream_t stream)
   cfg.numAttrs = CL > 1 ? 1 : 0;
   int max_walkers = sms / CL;
   if (CL > 1) {        // persistent kernel: no more clusters than the device can hold at once (a GPC with an odd SM count strands one)
-    static int max_clusters = -1;
-    if (max_clusters < 0) {
-      cfg.gridDim = dim3(kNumSMsB200);
+    static const int max_clusters = [&] {
+      cudaLaunchConfig_t q = cfg;
+      q.gridDim = dim3(kNumSMsB200);
       int n = 0;
-      if (cudaOccupancyMaxActiveClusters(&n, gemm_tcgen05_kernel<BLOCK_N, ACT, CL, EW>, &cfg) != cudaSuccess || n <= 0) n = sms / CL;
-      max_clusters = n;
-    }
+      if (cudaOccupancyMaxActiveClusters(&n, gemm_tcgen05_kernel<BLOCK_N, ACT, CL, EW>, &q) != cudaSuccess || n <= 0) n = kNumSMsB200 / CL;
+      return n;
+    }();
     if (max_clusters < max_walkers) max_walkers = max_clusters;
   }
   const int walkers = units < max_walkers ? units : max_walkers;
@@ -545,6 +553,16 @@ int launch_gemm(const f5_gemm_args& a, const GemmParams& p, cudaStream_t stream)
 }
 
 }  // namespace f5
+
+F5_DEFINE_DIAG_SETTER(f5_diag_set_gemm)
+int f5_diag_set_attn(void* mapped);   // attn_tcgen05.cu
+
+// Fault record of the mbarrier watchdog: `mapped` is host memory the device can write (pinned, >= 40 x 8 bytes, zeroed);
+// NULL switches reporting off.  See f5_common.cuh for the layout.
+extern "C" int f5_diag_enable(void* mapped) {
+  int rc = f5_diag_set_gemm(mapped);
+  return rc != 0 ? rc : f5_diag_set_attn(mapped);
+}
 
 extern "C" int f5_gemm_bf16(const f5_gemm_args* a, void* stream) {
   using namespace f5;

@@ -128,8 +128,9 @@ class UtteranceInput:
     text_ids: torch.Tensor    # int64 [nt], vocabulary ids (no padding)
     n: int                    # total frames (duration after the max/clamp rules)
     cond_len: int             # frames where cond_mask is true (lens after max with text_lens)
-    y0: torch.Tensor          # fp32 [n, mel] initial noise
+    y0: torch.Tensor | None   # fp32 [n, mel] initial noise injected by the caller (parity tests); None: drawn on the device
     edit_mask: torch.Tensor | None = None   # bool [>= cond_len]
+    noise_seed: int = 0       # 64-bit Philox key of the device draw when y0 is None (f5_randn_rows)
 
 
 class Workspace:
@@ -166,8 +167,22 @@ class Workspace:
         # attention work items live in ONE device buffer per workspace: the captured step graph holds its address and the
         # (padded) item count, so batches of other utterance lengths that fit the same rows replay the same graph
         self.tiles_buf = torch.zeros(2 * (R // 128 + 64), 4, device=device, dtype=I32)
+        self.row_utt = torch.full((R,), -1, device=device, dtype=I32)
         self.graphs: dict[tuple, torch.cuda.CUDAGraph] = {}
         self.graph_launches: dict[tuple, int] = {}
+        # Pinned host mirrors of the per-batch inputs, allocated once per workspace (cudaHostAlloc of tens of MB per batch was
+        # a measurable part of the end-to-end step, and a fresh pinned buffer per batch keeps the host allocator busy while
+        # the GPU runs).  `upload_done` marks the end of the last batch's H2D copies: the mirrors are rewritten only after it.
+        self._pinned: dict[str, torch.Tensor] = {}
+        self.upload_done: torch.cuda.Event | None = None
+        self.generation = 0                     # bumped by every upload: a Staged batch is valid for ONE generation
+
+    def pinned(self, name: str, shape: tuple, dtype) -> torch.Tensor:
+        t = self._pinned.get(name)
+        if t is None or t.shape != tuple(shape) or t.dtype != dtype:
+            t = torch.zeros(*shape, dtype=dtype).pin_memory()
+            self._pinned[name] = t
+        return t
 
 
 class F5Engine:
@@ -204,17 +219,42 @@ class F5Engine:
         return ws
 
     def upload(self, utts: list[UtteranceInput], layout: PackedLayout, steps: int, sway: float | None) -> Workspace:
-        """Stage the per-batch inputs in pinned host memory and copy them to the device (H2D on the current stream)."""
+        """Stage the per-batch inputs through the workspace's pinned host mirrors and copy them to the device (H2D on the
+        current stream).  The initial noise is drawn on the device (Philox, `f5_randn_rows`) unless the caller injects `y0`;
+        a prompt mel that is already on the device never visits the host."""
         cfg, R = self.cfg, layout.half_rows
-        ws = self.workspace(R)
         mel = cfg.mel_dim
-        pin = lambda *s, dt=F32: torch.zeros(*s, dtype=dt).pin_memory()  # noqa: E731
-        h_x, h_cond = pin(R, MELP), pin(R, MELP)
-        h_ids, h_flag = pin(2 * R, dt=I32), pin(R, dt=I32)
+        if steps > 128:
+            raise ValueError(f"steps={steps}: the hoisted time/AdaLN tables hold at most 128 Euler steps")
+        if max(layout.lengths) > cfg.max_pos:
+            raise ValueError(f"an utterance of {max(layout.lengths)} frames exceeds max_pos={cfg.max_pos} (cfm.py:137 clamps at 4096)")
+        emb_rows = self.w.emb.shape[0]
+        for u in utts:                                               # nn.Embedding would raise IndexError (dit.py:56)
+            if u.text_ids.numel() and int(u.text_ids.max()) + 1 >= emb_rows:
+                raise IndexError(f"token id {int(u.text_ids.max())} is outside the text embedding ({emb_rows - 1} entries)")
+        ws = self.workspace(R)
+        if ws.upload_done is not None:
+            ws.upload_done.synchronize()                             # the previous batch's H2D copies have left the mirrors
+        ws.generation += 1
+        inject = any(u.y0 is not None for u in utts)
+        if inject and not all(u.y0 is not None for u in utts):
+            raise ValueError("y0 must be given for every utterance of a batch or for none")
+        host_cond = any(not (u.cond.is_cuda and u.edit_mask is None) for u in utts)
+        h_ids, h_flag = ws.pinned("ids", (2 * R,), I32), ws.pinned("flag", (R,), I32)
+        h_ids.zero_()
+        h_flag.zero_()
+        h_x = h_cond = None
+        if inject:
+            h_x = ws.pinned("x0", (R, MELP), F32)
+            h_x.zero_()
+        if host_cond:
+            h_cond = ws.pinned("cond", (R, MELP), F32)
+            h_cond.zero_()
         dev_conds = []
         for u, s in zip(utts, layout.starts):
             n = u.n
-            h_x[s:s + n, :mel] = u.y0[:n].float().cpu()
+            if inject:
+                h_x[s:s + n, :mel] = u.y0[:n].float().cpu()
             F_ = min(u.cond.shape[0], n)
             mask = torch.zeros(n, dtype=torch.bool)
             mask[: min(u.cond_len, n)] = True
@@ -230,33 +270,55 @@ class F5Engine:
                 h_cond[s:s + n, :mel] = torch.where(mask[:, None], c, torch.zeros_like(c))
             nt = min(u.text_ids.numel(), n)                      # dit.py:48-51: +1, truncate to n, filler 0
             h_ids[s:s + nt] = (u.text_ids[:nt] + 1).to(I32)
-        ws.x0.copy_(h_x, non_blocking=True)
-        ws.cond.copy_(h_cond, non_blocking=True)
+        h_pos = ws.pinned("row_pos", (2 * R,), I32)
+        h_pos.copy_(layout.row_pos)
+        h_utt = ws.pinned("row_utt", (R,), I32)
+        h_utt.copy_(layout.row_utt)
+        ws.row_pos.copy_(h_pos, non_blocking=True)
+        ws.row_utt.copy_(h_utt, non_blocking=True)
+        if inject:
+            ws.x0.copy_(h_x, non_blocking=True)
+        else:
+            h_seed = ws.pinned("seeds", (max(len(utts), 1),), torch.int64)
+            h_seed[: len(utts)] = torch.tensor([((u.noise_seed + (1 << 63)) % (1 << 64)) - (1 << 63) for u in utts], dtype=torch.int64)
+            ws.seeds = h_seed.to(self.device, non_blocking=True)
+            ops.randn_rows(ws.x0, mel, ws.row_pos, ws.row_utt, ws.seeds, M=R)      # cfm.py:181-186 on the device
+        if host_cond:
+            ws.cond.copy_(h_cond, non_blocking=True)
+        else:
+            ws.cond.zero_()
         for s, f, c in dev_conds:
             ws.cond[s:s + f, :mel].copy_(c[:f])
         ws.ids.copy_(h_ids, non_blocking=True)
         ws.cond_flag.copy_(h_flag, non_blocking=True)
-        ws.row_pos.copy_(layout.row_pos.pin_memory(), non_blocking=True)
         n_items = layout.attn_tiles.shape[0]
         padded = (n_items + 7) // 8 * 8                # item count is baked into the step graph: pad it to a multiple of 8 ...
         if padded > ws.tiles_buf.shape[0]:
             ws.tiles_buf = torch.zeros(padded + 64, 4, device=self.device, dtype=I32)
             ws.graphs.clear()
-        h_tiles = torch.zeros(padded, 4, dtype=I32)                # ... with items of zero query rows, which the kernel skips
+        h_tiles = ws.pinned("tiles", (ws.tiles_buf.shape[0], 4), I32)
+        h_tiles.zero_()                                            # ... with items of zero query rows, which the kernel skips
         h_tiles[:n_items] = layout.attn_tiles
-        ws.tiles_buf[:padded].copy_(h_tiles)                       # a few KB: plain blocking copies (no host-buffer lifetime to reason about)
+        ws.tiles_buf[:padded].copy_(h_tiles[:padded], non_blocking=True)
         ws.tiles = ws.tiles_buf[:padded]
-        ws.segs = layout.seg_rows.to(self.device)
-        ws.sumsq = torch.zeros(ws.segs.shape[0], cfg.text_inner, device=self.device, dtype=F32)
+        nseg = layout.seg_rows.shape[0]
+        h_seg = ws.pinned("segs", (nseg, 2), I32)
+        h_seg.copy_(layout.seg_rows)
+        ws.segs = h_seg.to(self.device, non_blocking=True)
+        ws.sumsq = torch.zeros(nseg, cfg.text_inner, device=self.device, dtype=F32)
         t = sway_time_grid(steps, sway)
-        h_t = pin(ws.tgrid.shape[0])
+        h_t = ws.pinned("tgrid", (ws.tgrid.shape[0],), F32)
+        h_t.zero_()
         h_t[: steps + 1] = t
-        h_dt = pin(ws.dts.shape[0])
+        h_dt = ws.pinned("dts", (ws.dts.shape[0],), F32)
+        h_dt.zero_()
         h_dt[:steps] = t[1:] - t[:-1]                          # torchdiffeq Euler: dt = t1 - t0 in the grid dtype
         ws.tgrid.copy_(h_t, non_blocking=True)
         ws.dts.copy_(h_dt, non_blocking=True)
-        ws.h2d_bytes = sum(v.numel() * v.element_size() for v in (h_x, h_cond, h_ids, h_flag, h_t, h_dt)) + \
-            layout.row_pos.numel() * 4
+        ws.upload_done = torch.cuda.Event()
+        ws.upload_done.record()
+        moved = [h_ids, h_flag, h_pos, h_utt, h_tiles[:padded], h_seg, h_t, h_dt] + ([h_x] if inject else []) + ([h_cond] if host_cond else [])
+        ws.h2d_bytes = sum(v.numel() * v.element_size() for v in moved) + (0 if inject else 8 * len(utts))
         return ws
 
     # ------------------------------------------------------------------------------------------ hoisted work
@@ -358,10 +420,13 @@ class F5Engine:
         return ws, layout
 
     @torch.inference_mode()
-    def compute(self, ws: Workspace, steps: int = 32, cfg_strength: float = 2.0) -> None:
+    def compute(self, ws: Workspace, steps: int = 32, cfg_strength: float = 2.0, generation: int | None = None) -> None:
         """Device-resident hot path on a staged batch: hoisted work, the Euler loop, prompt re-insert (cfm.py:160-204)."""
         if cfg_strength < 1e-5:
             raise NotImplementedError("cfg_strength < 1e-5 (single-branch sampling, cfm.py:170-171) is not on the served path")
+        if generation is not None and generation != ws.generation:
+            raise RuntimeError("this staged batch was overwritten: another batch of the same packed size was staged into its "
+                               "workspace before it ran (stage -> run must not interleave with another stage of the same size)")
         ws.x.copy_(ws.x0)
         self.hoist(ws, steps)
         self.run_steps(ws, steps, cfg_strength)

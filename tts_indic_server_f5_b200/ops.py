@@ -124,6 +124,13 @@ def cfg_euler(x, pred, half_rows: int, C_: int, row_pos, dts, step: int, cfg_str
          float(cfg_strength), ptr(xb), _ld(xb), C_pad, stream_ptr())
 
 
+def randn_rows(x, C_: int, row_pos, row_utt, utt_seed, M: int | None = None) -> None:
+    """x[row, :C] = N(0, 1) noise of (utt_seed[row_utt[row]], row_pos[row], channel); gap rows zero (f5_randn_rows)."""
+    assert x.dtype == F32 and row_pos.dtype == I32 and row_utt.dtype == I32 and utt_seed.dtype == torch.int64
+    call("f5_randn_rows", ptr(x), _ld(x), x.shape[0] if M is None else M, C_, ptr(row_pos), ptr(row_utt), ptr(utt_seed),
+         stream_ptr())
+
+
 def time_sinus(t, freqs, out) -> None:
     assert t.dtype == F32 and freqs.dtype == F32 and out.dtype == BF16
     call("f5_time_sinus", ptr(t), t.shape[0], ptr(freqs), 2 * freqs.shape[0], ptr(out), _ld(out), stream_ptr())

@@ -77,6 +77,7 @@ class Request:
     fix_duration: float | None = None
     cross_fade_duration: float = 0.15
     chunks: list[str] = field(default_factory=list)
+    seed: int = 0                  # base key of this request's noise (chunk i draws with utterance_seed(seed, i))
 
 
 class RequestScheduler:
@@ -93,23 +94,28 @@ class RequestScheduler:
         self.last_packs: list[list[int]] = []
 
     def submit(self, ref_audio, ref_text: str, gen_text: str, speed: float = 1.0, fix_duration: float | None = None,
-               cross_fade_duration: float = 0.15) -> int:
+               cross_fade_duration: float = 0.15, seed: int | None = None) -> int:
+        """Queue one `infer_process`-shaped request.  `seed` fixes its noise (same value => same audio as
+        `infer_process(..., seed=seed)`); by default every request is a fresh draw like the reference's (cfm.py:186)."""
+        from .api import fresh_noise_seed
         audio, sr = ref_audio
         max_chars = int(len(ref_text.encode("utf-8")) / (audio.shape[-1] / sr) * (25 - audio.shape[-1] / sr))   # utils_infer.py:377
         req = Request(self._next, audio, sr, ref_text, gen_text, speed, fix_duration, cross_fade_duration,
-                      T.chunk_text(gen_text, max_chars=max_chars))
+                      T.chunk_text(gen_text, max_chars=max_chars), fresh_noise_seed() if seed is None else seed)
         self._next += 1
         self.pending.append(req)
         return req.rid
 
     def run(self) -> dict[int, tuple[np.ndarray, int, np.ndarray]]:
         """-> {request id: (wave fp32, 24000, mel [100, F])}, the reference's `infer_process` triple per request."""
+        from .api import utterance_seed
         reqs, self.pending = self.pending, []
         specs, owner = [], []
         for r in reqs:
             for ci, chunk in enumerate(r.chunks):
                 specs.append(UtteranceSpec(audio=r.audio, ref_text=r.ref_text, gen_text=chunk, duration=None, noise_index=ci,
-                                           meta={"sr": r.sr, "speed": r.speed, "fix_duration": r.fix_duration}))
+                                           meta={"sr": r.sr, "speed": r.speed, "fix_duration": r.fix_duration,
+                                                 "noise_seed": utterance_seed(r.seed, ci)}))
                 owner.append((r.rid, ci))
         if not specs:
             return {}

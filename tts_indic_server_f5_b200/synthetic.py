@@ -41,6 +41,23 @@ def initial_noise(n_frames: int, index: int = 0, seed: int = 1234) -> torch.Tens
     return torch.randn(n_frames, N_MELS, generator=g, dtype=torch.float32)
 
 
+def reference_noise(specs) -> list[torch.Tensor]:
+    """The injected noise of every parity comparison (golden vectors, oracle runs, smoke): one CPU draw per utterance,
+    seed 1234 + noise_index.  The product's own default is a fresh device draw per request (api.fresh_noise_seed)."""
+    return [initial_noise(4096, s.noise_index) for s in specs]
+
+
+def forward_inputs(n: int, vocab_size: int, prompt_frames: int = 469, nt: int = 300):
+    """Seeded inputs of one full-size DiT forward pair (tests/golden/full_fwd.npz stores only the reference's OUTPUTS):
+    x [1, n, 100] noise-like state, cond [1, n, 100] log-mel-like prompt (zero past `prompt_frames`), text ids [1, nt]."""
+    g = torch.Generator("cpu").manual_seed(1000 + n)
+    x = torch.randn(1, n, N_MELS, generator=g)
+    cond = torch.randn(1, n, N_MELS, generator=g) * 1.5 - 2.0
+    cond[:, prompt_frames:] = 0
+    text = torch.randint(0, vocab_size, (1, nt), generator=g)
+    return x, cond, text
+
+
 @dataclass
 class UtteranceSpec:
     """One synthesis request at boundary #2 level: prompt wave + texts + (optional) explicit duration."""
