@@ -154,11 +154,11 @@ int f5_mel_frames(const float* wave, const int32_t* seg, int32_t num_segs, int32
 
 /* Fault record.  Every mbarrier wait in the tcgen05 kernels carries a watchdog: a pipeline that makes no progress for 4 s of
  * wall time traps (the launch fails with cudaErrorLaunchFailure) instead of hanging the GPU.  Before trapping, the waiting
- * thread writes 40 64-bit words into `mapped` — pinned host memory the device can address (e.g. cudaHostAlloc; zero it first) —
- * which stays readable on the host after the CUDA context has died: [0] claimed flag, [1] magic 0x46355744, [2] gridDim.x |
- * blockDim.x << 32, [3] blockIdx.x | threadIdx.x << 32, [4] barrier shared-memory address | parity << 32, [5] dynamic smem
- * bytes | cluster rank << 32, [6] ns waited, [8..40) raw state of the CTA's barrier block.  NULL switches it off.  The
- * reference has no counterpart (torch raises the CUDA error; core/managers.py:78-80 logs and re-raises). */
+ * thread writes one 16-byte record into `mapped` — pinned host memory the device can address (e.g. cudaHostAlloc; >= 512 bytes,
+ * zeroed) — which stays readable on the host after the CUDA context has died: u32[0] = 0xF5D00000 | kernel family (1 GEMM,
+ * 2 attention), u32[1] = blockIdx.x | gridDim.x << 16, u32[2] = threadIdx.x | blockDim.x << 16, u32[3] = barrier shared-memory
+ * address | parity << 31 (soak builds with -DF5_DIAG_FULL=1 append the raw state of every barrier of the CTA).  NULL switches it
+ * off.  The reference has no counterpart (torch raises the CUDA error; core/managers.py:78-80 logs and re-raises). */
 int f5_diag_enable(void* mapped);
 
 /* Library / device info. */

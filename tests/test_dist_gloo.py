@@ -51,3 +51,71 @@ def test_shard_and_gather_world2():
     assert sorted(out) == list(range(len(lens)))
     for i, n in enumerate(lens):
         assert out[i] == (256 * (n - 1), float(i), float(i))
+
+
+def _worker_plan(rank, world, port, lens, q):
+    """The bench's N > 1 path on CPU: every rank derives the same shard plan from the full list (no communication), produces its
+    share pack by pack, and the persistent-buffer gatherer lands everything on rank 0."""
+    from tts_indic_server_f5_b200.dist import WaveGatherer, shard_plan
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    plan = shard_plan(lens, world, max_rows=2 * 1024)
+    samples = [sum(256 * (lens[i] - 1) for i in part) for part in plan["parts"]]
+    g = WaveGatherer(samples, "cpu")
+    mine = plan["parts"][rank]
+    for step in range(2):                                   # the buffers are reused across steps
+        parts = []
+        for pack in plan["packs"][rank]:                    # packs hold LOCAL positions into this rank's share
+            for j in pack:
+                i = mine[j]
+                parts.append(torch.full((256 * (lens[i] - 1),), float(100 * step + i)))
+        g.gather(torch.cat(parts) if parts else torch.zeros(0))
+        host = g.to_host()
+    if rank == 0:
+        out = {}
+        for r, flat in enumerate(host):
+            off = 0
+            for pack in plan["packs"][r]:
+                for j in pack:
+                    i = plan["parts"][r][j]
+                    n = 256 * (lens[i] - 1)
+                    out[i] = (float(flat[off]), float(flat[off + n - 1]))
+                    off += n
+            assert off == flat.size
+        q.put((out, plan["imbalance"], [len(p) for p in plan["packs"]]))
+    else:
+        assert host is None
+    dist.destroy_process_group()
+
+
+def test_shard_plan_and_persistent_gather_world2():
+    lens = [300, 120, 450, 90, 333, 210, 64]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_plan, args=(r, 2, port, lens, q)) for r in range(2)]
+    [p.start() for p in procs]
+    out, imb, npacks = q.get(timeout=120)
+    [p.join(timeout=60) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    assert sorted(out) == list(range(len(lens)))
+    assert all(v == (100.0 + i, 100.0 + i) for i, v in out.items())          # second step's values: buffers really were reused
+    assert 1.0 <= imb < 1.25 and all(n >= 1 for n in npacks)
+
+
+def test_shard_plan_covers_c4_once():
+    from tts_indic_server_f5_b200 import synthetic as S
+    from tts_indic_server_f5_b200.dist import shard_plan
+    from tts_indic_server_f5_b200.scheduler import pack_rows
+    g = torch.Generator().manual_seed(1)
+    lens = [469 + int(torch.randint(560, 941, (1,), generator=g)) for _ in range(512)]
+    for world in (2, 4, 8):
+        plan = shard_plan(lens, world, max_rows=180224)
+        seen = sorted(i for part in plan["parts"] for i in part)
+        assert seen == list(range(512))
+        for r in range(world):
+            local = sorted(j for p in plan["packs"][r] for j in p)
+            assert local == list(range(len(plan["parts"][r])))
+            for p in plan["packs"][r]:
+                assert pack_rows([lens[plan["parts"][r][j]] for j in p]) <= 180224
+        assert plan["imbalance"] < 1.01                                       # LPT on 512 items: well under 1 %

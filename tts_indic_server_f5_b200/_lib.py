@@ -129,14 +129,12 @@ def read_diag() -> dict | None:
     w = _diag_buf.numpy().view("uint32")
     if (int(w[0]) & 0xFFF00000) != 0xF5D00000:
         return None
-    block_dim, smem_kib = int(w[0]) & 0xFFFFF, (int(w[2]) >> 16) & 0xFFFF
-    kernel = {(384, 128): "attn_d64_kernel"}.get((block_dim, smem_kib))
-    if kernel is None:
-        kernel = f"gemm_tcgen05_kernel ({'8' if block_dim == 384 else '4'} epilogue warps, {smem_kib} KiB smem)"
+    block_dim = int(w[2]) >> 16
+    kernel = {1: f"gemm_tcgen05_kernel ({'8' if block_dim == 384 else '4'} epilogue warps)", 2: "attn_d64_kernel"}.get(int(w[0]) & 0xFFFFF, "?")
     bar = int(w[3]) & 0x7FFFFFFF
     rec = {"kernel": kernel, "block_dim": block_dim, "grid_dim": int(w[1]) >> 16, "block": int(w[1]) & 0xFFFF,
-           "thread": int(w[2]) & 0xFFF, "warp": (int(w[2]) & 0xFFF) // 32, "cluster_rank": (int(w[2]) >> 12) & 0xF,
-           "dynamic_smem_kib": smem_kib, "barrier_smem_addr": bar, "barrier_slot": (bar & 255) // 8, "parity": int(w[3]) >> 31}
+           "thread": int(w[2]) & 0xFFFF, "warp": (int(w[2]) & 0xFFFF) // 32, "barrier_smem_addr": bar,
+           "barrier_slot": (bar & 255) // 8, "parity": int(w[3]) >> 31}
     q = _diag_buf.numpy().view("uint64")
     if int(q[2]) != 0:
         rec["waited_ns"] = int(q[3])

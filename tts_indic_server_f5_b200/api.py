@@ -320,7 +320,7 @@ class Synthesizer:
 
     @torch.inference_mode()
     def stage(self, specs: list[UtteranceSpec], nfe_step=nfe_step, sway_sampling_coef=sway_sampling_coef, speed=speed,
-              fix_duration=fix_duration, y0: list | None = None, noise_seed: int | None = None) -> "Staged":
+              fix_duration=fix_duration, y0: list | None = None, noise_seed: int | None = None, slot: int = 0) -> "Staged":
         """Host side + H2D of one request batch: tokenise, duration rule, prompt RMS, pinned copies of prompt audio / tables,
         prompt mel and initial noise on the device.  After this the batch is resident in HBM.  `y0` (one [>= n_i, 100] tensor
         per utterance) injects the noise instead (parity tests); `noise_seed` fixes the device draw (default: a fresh one per
@@ -360,7 +360,7 @@ class Synthesizer:
             n = min(max(lens_i + 1, p.duration), 4096)
             utts.append(UtteranceInput(cond=m, text_ids=tid, n=n, cond_len=lens_i, y0=None if y0 is None else y0[i],
                                        noise_seed=p.noise_seed if p.noise_seed is not None else utterance_seed(base, p.noise_index)))
-        ws, layout = model.engine.stage(utts, nfe_step, sway_sampling_coef)
+        ws, layout = model.engine.stage(utts, nfe_step, sway_sampling_coef, slot)
         h2d += ws.h2d_bytes
         veng = self.vocoder.engine                                                # vocoder rows = generated frames only
         frames = [n - p.ref_len for n, p in zip(layout.lengths, preps)]
@@ -384,8 +384,8 @@ class Synthesizer:
 
     def generate_device(self, specs: list[UtteranceSpec], nfe_step=nfe_step, cfg_strength=cfg_strength,
                         sway_sampling_coef=sway_sampling_coef, speed=speed, fix_duration=fix_duration,
-                        y0: list | None = None, noise_seed: int | None = None):
-        st = self.stage(specs, nfe_step, sway_sampling_coef, speed, fix_duration, y0, noise_seed)
+                        y0: list | None = None, noise_seed: int | None = None, slot: int = 0):
+        st = self.stage(specs, nfe_step, sway_sampling_coef, speed, fix_duration, y0, noise_seed, slot)
         wav = self.run(st, cfg_strength)
         return wav, st.offs, st.frames, st.total, st.ws, st.layout, st.preps
 

@@ -27,6 +27,7 @@
 //     the groups drift into lockstep (measured: both idle the MUFU for ~1100 of 3400 cycles per tile).
 //     MMA issue order per step a:  QK_A(a+1) | QK_B(a) | PV_B(a-1) | PV_A(a).
 // TMEM: S_A | S_B | P_A | P_B | O_A | O_B = 128+128+64+64+64+64 = 512 columns.
+#define F5_DIAG_TAG 2u
 #include "f5_common.cuh"
 #include "../../include/f5_b200.h"
 #include <cstdlib>
@@ -291,16 +292,23 @@ attn_d64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnParams p
 #if F5_WAIT_ALL_LANES
       if (nxt.valid()) issue_qk(0, nxt, a + 1, iq0, tq0);          // QK_A(a+1): at the start of softmax_A(a)
       mbar_wait(a_gate, a & 1);                                    // softmax_A(a) is past its row max
-#else
-      // The gate is waited for BEFORE QK_A(a+1) is issued (round 1 had it after): group A reaches gate(a+1) only through
-      // S_A(a+1), so with this order a_gate can never complete a second phase while this warp still waits for the first.
-      // It costs QK_A(a+1) one row-max pass (~200 cycles) of head start out of the ~2000 it has before softmax_A(a) ends.
-      mbar_wait_warp(a_gate, a & 1, leader);                       // softmax_A(a) is past its row max
-      if (nxt.valid()) issue_qk(0, nxt, a + 1, iq0, tq0);          // QK_A(a+1): during softmax_A(a)
-#endif
       if (cur.ngroups == 2) issue_qk(1, cur, a, iq1, tq1);         // QK_B(a): group B runs half a tile behind A
       if (leader) umma_commit(&k_empty[a % ATT_KV_STAGES]);        // QK_A(a) (issued a step ago) and QK_B(a) retired -> K stage reusable
       __syncwarp();
+#else
+      // Round 1 issued QK_A(a+1) BEFORE waiting for gate(a).  That made a_gate the one barrier whose NEXT phase did not depend
+      // on its waiter: group A reaches gate(a+1) through S_A(a+1), which was already on its way.  When this warp's try_wait
+      // on gate(a) slept through the phase flip (a try_wait may return late — it suspends the thread for a system-dependent
+      // time), group A finished tile a, took S_A(a+1), passed its row max and completed gate(a+1): the parity this warp
+      // waits for then reads "not complete" for ever.  The soak run's watchdog record shows exactly that (warp 9 stuck on
+      // a_gate with every other barrier of the CTA idle; profiles/r02_soak_ab.md).  Now the gate comes first; QK_B(a), which
+      // group B needs soonest, goes out right behind it and QK_A(a+1) follows — group A needs S_A(a+1) only ~1500 cycles later.
+      mbar_wait_warp(a_gate, a & 1, leader);                       // softmax_A(a) is past its row max
+      if (cur.ngroups == 2) issue_qk(1, cur, a, iq1, tq1);         // QK_B(a): group B runs half a tile behind A
+      if (leader) umma_commit(&k_empty[a % ATT_KV_STAGES]);        // QK_A(a) (issued a step ago) and QK_B(a) retired -> K stage reusable
+      __syncwarp();
+      if (nxt.valid()) issue_qk(0, nxt, a + 1, iq0, tq0);          // QK_A(a+1): during softmax_A(a)
+#endif
       if (lane == 0) { F5_TRACE(1, ev); }
       ++ev;
       if (a > 0) {

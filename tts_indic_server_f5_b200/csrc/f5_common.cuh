@@ -42,14 +42,17 @@ __device__ __forceinline__ bool elect_one() {
 // ------------------------------------------------------------------ device-side fault record
 // One pointer per translation unit (no -rdc): set by f5_diag_enable() through the F5_DEFINE_DIAG_SETTER each .cu defines.
 // The record is ONE 16-byte store (any timed-out thread's record is a valid one; they are all stuck on the same pipeline):
-//   u32[0] = 0xF5D00000 | blockDim.x          u32[1] = blockIdx.x | gridDim.x << 16
-//   u32[2] = threadIdx.x | cluster cta rank << 12 | dynamic smem KiB << 16     u32[3] = barrier smem address | parity << 31
+//   u32[0] = 0xF5D00000 | F5_DIAG_TAG (one per .cu: which kernel family)     u32[1] = blockIdx.x | gridDim.x << 16
+//   u32[2] = threadIdx.x | blockDim.x << 16                                  u32[3] = barrier smem address | parity << 31
 // It is inlined at every wait (a call inside a setmaxnreg region does not register-allocate), so it is kept to a dozen
 // instructions: the attention kernel is sensitive to its instruction footprint.  -DF5_DIAG_FULL=1 (soak builds) appends
 // u64[2] = claim flag, u64[3] = ns waited, u64[8..40) = the 32 eight-byte words at (barrier & ~255): the raw state of every
 // mbarrier of the CTA (each kernel keeps its barriers inside one 256-byte aligned block).
 #ifndef F5_DIAG_FULL
 #define F5_DIAG_FULL 0
+#endif
+#ifndef F5_DIAG_TAG
+#define F5_DIAG_TAG 0u        // 1: gemm_tcgen05.cu, 2: attn_tcgen05.cu
 #endif
 #ifndef F5_DIAG
 #define F5_DIAG 1             // 0: trap without a record (A/B builds that measure what the record costs)
@@ -64,11 +67,8 @@ __device__ __forceinline__ void diag_report_and_trap(uint32_t bar, uint32_t pari
 #if F5_DIAG
   unsigned long long* d = f5_diag_ptr;
   if (d != nullptr) {
-    uint32_t dyn, rank;
-    asm volatile("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn));
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
-    const uint4 rec = make_uint4(0xF5D00000u | blockDim.x, blockIdx.x | (gridDim.x << 16),
-                                 threadIdx.x | (rank << 12) | ((dyn >> 10) << 16), bar | (parity << 31));
+    const uint4 rec = make_uint4(0xF5D00000u | F5_DIAG_TAG, blockIdx.x | (gridDim.x << 16), threadIdx.x | (blockDim.x << 16),
+                                 bar | (parity << 31));
     asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(d), "r"(rec.x), "r"(rec.y), "r"(rec.z), "r"(rec.w) : "memory");
 #if F5_DIAG_FULL
     if (atomicCAS(d + 2, 0ull, 1ull) == 0ull) {
@@ -141,18 +141,44 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   mbar_wait_slow(smem_u32(bar), parity);
 }
 // Wait of a whole producer / MMA warp that walks its loop warp-uniformly with ONE elected lane issuing (TMA, tcgen05.mma,
-// commits).  Only that lane polls the barrier; the others park at the __syncwarp.  If every lane polled for itself (the
-// round-1 form), a lane that is still inside try_wait when the leader has already moved on is exposed to the phases the
-// leader's own next instruction sets in motion: the leader's TMA lands / its MMAs retire and flip the same barrier AGAIN
-// within ~1 us, the late lane then sees the parity it is waiting for as "not yet complete", and the warp is stuck at the next
-// __syncwarp for good — a parity wait must never be able to fall two phases behind, and with 32 independent pollers nothing
-// in the protocol guaranteed that.  With one poller the thread that observes the phase is the thread that advances it.
+// commits).  All 32 lanes poll together and the warp leaves only when EVERY lane has seen the phase complete in the same
+// poll (one VOTE.ALL on top of the try_wait; the loop condition is warp-uniform, so there is no divergence and the issue
+// instructions that follow stay on the uniform datapath).  A parity wait is only correct while the waiter can never be
+// two phases behind; with 32 independent pollers (the round-1 form) that would have to hold per LANE, with the vote it has
+// to hold per WARP, which the kernels' protocols guarantee: for every barrier such a warp waits on, the barrier's next
+// phase cannot start before this warp has issued something AFTER the wait (see the a_gate note in attn_tcgen05.cu for the
+// one place where round 1 violated that).
+// F5_WAIT_MODE: 0 = vote (default), 1 = round-1 form (every lane for itself; A/B soak builds), 2 = only the elected lane
+// polls, the others park at a __syncwarp (measured ~20 % slower on the attention kernel: a divergent region per wait).
+#ifndef F5_WAIT_MODE
+#define F5_WAIT_MODE (F5_WAIT_ALL_LANES ? 1 : 0)
+#endif
 __device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, bool leader) {
-#if F5_WAIT_ALL_LANES
+#if F5_WAIT_MODE == 1
   mbar_wait(bar, parity);
-#else
+#elif F5_WAIT_MODE == 2
   if (leader) mbar_wait(bar, parity);
   __syncwarp();
+#else
+  const uint32_t addr = smem_u32(bar);
+  long long t0 = 0;
+  for (uint32_t polls = 1;; ++polls) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t}\n"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (__all_sync(0xffffffffu, ok != 0)) return;
+    if ((polls & 4095u) == 0) {
+      long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t0 == 0) t0 = now;
+      if (now - t0 > F5_WATCHDOG_NS) diag_report_and_trap(addr, parity, now - t0);
+    }
+  }
 #endif
 }
 // Variants on a 32-bit shared-window address computed ONCE by the caller (the generic-pointer forms re-derive the window

@@ -9,6 +9,7 @@
 //
 // Tiles are walked n-fastest so that the CTAs running concurrently share A row-blocks through L2 while B (weights,
 // a few MB) stays L2-resident.
+#define F5_DIAG_TAG 1u
 #include "f5_common.cuh"
 #include "../../include/f5_b200.h"
 #include <cstdlib>

@@ -202,23 +202,25 @@ class F5Engine:
         self.cfg, self.device = cfg, dev
         self.w = DiTWeights(sd, cfg, self.device)
         self.use_graphs = use_graphs
-        self._ws: dict[int, Workspace] = {}          # LRU over row counts (insertion order = recency)
+        self._ws: dict[tuple, Workspace] = {}        # LRU over (row count, slot) (insertion order = recency)
         self.max_workspaces = 4                       # ~30 KB of buffers per row: C2 (159 k rows) is 4.7 GB
         self.max_graphs_per_workspace = 8
         self.graph_captures = 0                       # statistics: captures vs replays of the step graph
         self.graph_replays = 0
 
     # ------------------------------------------------------------------------------------------ batch set-up
-    def workspace(self, R: int) -> Workspace:
-        ws = self._ws.pop(R, None)
+    def workspace(self, R: int, slot: int = 0) -> Workspace:
+        """Buffers for a packed batch of R rows.  `slot` separates batches of the SAME size that must be resident at the same
+        time (several staged packs of one request batch); a stage into an occupied (R, slot) takes the workspace over."""
+        ws = self._ws.pop((R, slot), None)
         if ws is None:
             while len(self._ws) >= self.max_workspaces:            # evict the least recently used size (and its graphs)
                 self._ws.pop(next(iter(self._ws)))
             ws = Workspace(self.cfg, R, 128, self.device)
-        self._ws[R] = ws
+        self._ws[(R, slot)] = ws
         return ws
 
-    def upload(self, utts: list[UtteranceInput], layout: PackedLayout, steps: int, sway: float | None) -> Workspace:
+    def upload(self, utts: list[UtteranceInput], layout: PackedLayout, steps: int, sway: float | None, slot: int = 0) -> Workspace:
         """Stage the per-batch inputs through the workspace's pinned host mirrors and copy them to the device (H2D on the
         current stream).  The initial noise is drawn on the device (Philox, `f5_randn_rows`) unless the caller injects `y0`;
         a prompt mel that is already on the device never visits the host."""
@@ -232,7 +234,7 @@ class F5Engine:
         for u in utts:                                               # nn.Embedding would raise IndexError (dit.py:56)
             if u.text_ids.numel() and int(u.text_ids.max()) + 1 >= emb_rows:
                 raise IndexError(f"token id {int(u.text_ids.max())} is outside the text embedding ({emb_rows - 1} entries)")
-        ws = self.workspace(R)
+        ws = self.workspace(R, slot)
         if ws.upload_done is not None:
             ws.upload_done.synchronize()                             # the previous batch's H2D copies have left the mirrors
         ws.generation += 1
@@ -413,10 +415,10 @@ class F5Engine:
 
     # ------------------------------------------------------------------------------------------ public
     @torch.inference_mode()
-    def stage(self, utts: list[UtteranceInput], steps: int = 32, sway_sampling_coef: float | None = -1.0):
+    def stage(self, utts: list[UtteranceInput], steps: int = 32, sway_sampling_coef: float | None = -1.0, slot: int = 0):
         """Host -> device: build the packed layout and copy this batch's inputs (pinned H2D).  No arithmetic."""
         layout = build_layout([u.n for u in utts])
-        ws = self.upload(utts, layout, steps, sway_sampling_coef)
+        ws = self.upload(utts, layout, steps, sway_sampling_coef, slot)
         return ws, layout
 
     @torch.inference_mode()

@@ -55,15 +55,20 @@ class VocosEngine:
         self.window = f32(vsd["head.istft.window"])
         self.spec_ld = (self.nout_pad + 127) // 128 * 128
         self._bufs: dict[int, dict] = {}
+        self.max_buffer_sets = 4
 
     def _buffers(self, Rv: int) -> dict:
-        b = self._bufs.get(Rv)
+        """Scratch for Rv vocoder rows; an LRU of a few sizes (a server sees a handful of length buckets: re-allocating and
+        zero-filling ~13 KB per row on every new length was a measurable part of a single-utterance request)."""
+        b = self._bufs.pop(Rv, None)
         if b is None:
             C, I = self.cfg.dim, self.cfg.intermediate_dim
             z = lambda r, c, dt: torch.zeros(r, c, device=self.device, dtype=dt)  # noqa: E731
             b = dict(melb=z(Rv, MELP, BF16), h=z(Rv, C, F32), v=z(Rv, C, F32), hb=z(Rv, C, BF16), ib=z(Rv, I, BF16),
                      spec=z(Rv, self.spec_ld, F32), frames=z(Rv, self.cfg.n_fft, F32))
-            self._bufs = {Rv: b}
+            while len(self._bufs) >= self.max_buffer_sets:
+                self._bufs.pop(next(iter(self._bufs)))
+        self._bufs[Rv] = b                                                  # most recently used last
         return b
 
     @staticmethod
