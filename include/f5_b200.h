@@ -161,6 +161,13 @@ int f5_mel_frames(const float* wave, const int32_t* seg, int32_t num_segs, int32
  * off.  The reference has no counterpart (torch raises the CUDA error; core/managers.py:78-80 logs and re-raises). */
 int f5_diag_enable(void* mapped);
 
+/* Programmatic dependent launch.  Every kernel of the library is launched with the programmatic-stream-serialization attribute
+ * and executes `griddepcontrol.wait` before it touches memory a predecessor may have written, so its set-up (barrier init, TMEM
+ * allocation, tensor-map prefetch) overlaps the previous kernel's tail; inside a captured CUDA graph the edges become programmatic
+ * dependencies.  Default on (environment F5_PDL=0 turns it off at load).  Returns the previous setting.  No reference counterpart:
+ * the reference launches ~40 torch kernels per DiT block with full stream serialization (model/modules.py:558-572). */
+int f5_set_pdl(int enabled);
+
 /* Library / device info. */
 int f5_device_check(void);      /* 0 if the current device is sm_100 */
 const char* f5_version(void);

@@ -351,7 +351,7 @@ def test_tts_manager_load_and_synthesize_vs_oracle(tiny_models, tmp_path):
         w.setnchannels(1); w.setsampwidth(2); w.setframerate(rate)
         w.writeframes(np.clip(np.round(pcm * 32767), -32768, 32767).astype("<i2").tobytes())
     ref_text = T.synthetic_indic_text(24, 1)
-    gen = ". ".join(T.synthetic_indic_text(50, 20 + i) for i in range(5)) + "."
+    gen = ". ".join(T.synthetic_indic_text(60, 20 + i) for i in range(14)) + "."
     mgr = api.TTSManager(state_dict=sd, vocoder_state_dict=vsd)
     mgr.load()
     assert mgr.model
@@ -427,3 +427,26 @@ def test_engine_rejects_what_it_cannot_hold(tiny_models):
     syn.stage(specs, noise_seed=2)                                            # same packed size: takes over the workspace
     with pytest.raises(RuntimeError, match="overwritten"):
         syn.run(st1)
+
+
+def test_programmatic_dependent_launch_is_bit_invisible(tiny_models):
+    """PDL (f5_set_pdl) only moves each kernel's set-up ahead of its predecessor's tail: eager launches and a freshly captured
+    step graph with it ON equal eager launches with it OFF bit for bit, over the whole path (sampler + vocoder)."""
+    from tts_indic_server_f5_b200 import _lib
+    cfg, vcfg, sd, vsd, model, voc = tiny_models
+    specs = S.workload("tiny3")
+    m2 = api.load_model(state_dict=sd)                       # own engine: own workspaces and graphs
+    syn = api.Synthesizer(m2, voc)
+    old = _lib.lib.f5_set_pdl(0)
+    try:
+        m2.engine.use_graphs = False
+        off = syn.generate(specs, nfe_step=6, noise_seed=21)
+        assert _lib.lib.f5_set_pdl(1) == 0
+        on_eager = syn.generate(specs, nfe_step=6, noise_seed=21)
+        m2.engine.use_graphs = True
+        on_graph = syn.generate(specs, nfe_step=6, noise_seed=21)      # captured now, with programmatic edges
+        on_replay = syn.generate(specs, nfe_step=6, noise_seed=21)
+    finally:
+        _lib.lib.f5_set_pdl(old)
+    for a, b, c, d in zip(off, on_eager, on_graph, on_replay):
+        assert np.array_equal(a, b) and np.array_equal(a, c) and np.array_equal(a, d)

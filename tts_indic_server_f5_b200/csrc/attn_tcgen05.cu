@@ -179,6 +179,8 @@ attn_d64_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnParams p
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();                                // set-up above overlapped the QKV GEMM's tail; its output is read below
+  pdl_launch();
 
   if (warp >= 8) {
    asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
@@ -545,6 +547,5 @@ extern "C" int f5_attention_d64(const void* qkv, int64_t ld, int32_t rows, int32
 #endif
   p.trace = g_trace_buf;
   const int grid = p.num_work < kNumSMsB200 ? p.num_work : kNumSMsB200;
-  attn_d64_kernel<<<grid, ATT_THREADS, ATT_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(tq, p);
-  return static_cast<int>(cudaGetLastError());
+  return static_cast<int>(f5_launch(attn_d64_kernel, dim3(grid), dim3(ATT_THREADS), ATT_SMEM, reinterpret_cast<cudaStream_t>(stream), tq, p));
 }

@@ -13,6 +13,8 @@ __global__ void __launch_bounds__(256) layernorm_mod_kernel(const float* __restr
                                                             float* __restrict__ y32, long long ldy32, int M,
                                                             const float* __restrict__ a, const float* __restrict__ b,
                                                             float a_off, float eps) {
+  pdl_wait();
+  pdl_launch();
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= M) return;
   const int lane = threadIdx.x & 31;
@@ -60,6 +62,8 @@ __global__ void __launch_bounds__(256) dwconv7_ln_kernel(const float* __restrict
                                                          const int* __restrict__ row_pos, const float* __restrict__ w,
                                                          const float* __restrict__ bias, const float* __restrict__ ln_w,
                                                          const float* __restrict__ ln_b, float eps) {
+  pdl_wait();
+  pdl_launch();
   constexpr int C = NV * 128;
   __shared__ float4 wT[7][NV * 32];
   __shared__ float4 cb[NV * 32], lw[NV * 32], lb[NV * 32];
@@ -133,6 +137,8 @@ constexpr int GRN_ROWS = 32;  // rows per block
 // slices; each thread walks its slice of the utterance's rows in order, the 4 slices are combined in a fixed order.
 __global__ void __launch_bounds__(256) grn_sumsq_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, int C,
                                                         const int* __restrict__ seg_rows, float* __restrict__ sumsq) {
+  pdl_wait();
+  pdl_launch();
   __shared__ float2 part[4][64];
   const int seg = blockIdx.y;
   const int row0 = seg_rows[2 * seg], n = seg_rows[2 * seg + 1];
@@ -158,6 +164,8 @@ __global__ void __launch_bounds__(256) grn_sumsq_kernel(const __nv_bfloat16* __r
 __global__ void grn_apply_kernel(__nv_bfloat16* __restrict__ x, long long ldx, int C, const int* __restrict__ seg_rows,
                                  const float* __restrict__ sumsq, const float* __restrict__ gamma,
                                  const float* __restrict__ beta) {
+  pdl_wait();
+  pdl_launch();
   __shared__ float red[32];
   __shared__ float mean_gx;
   const int seg = blockIdx.y;
@@ -193,6 +201,8 @@ __global__ void grn_apply_kernel(__nv_bfloat16* __restrict__ x, long long ldx, i
 __global__ void text_gather_pos_kernel(const int* __restrict__ ids, const int* __restrict__ row_pos,
                                        const float* __restrict__ emb, const float* __restrict__ pos_table, int max_pos,
                                        float* __restrict__ out, long long ldo, int M, int C) {
+  pdl_wait();
+  pdl_launch();
   const int row = blockIdx.x;
   if (row >= M) return;
   const int pos = row_pos[row];
@@ -214,6 +224,8 @@ __global__ void __launch_bounds__(256) pack_bf16_kernel(const float* __restrict_
                                                         __nv_bfloat16* __restrict__ dst, long long ldd, int dst_col,
                                                         int M, int C, int C_pad, const int* __restrict__ src_rows,
                                                         const int* __restrict__ row_pos) {
+  pdl_wait();
+  pdl_launch();
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= M) return;
   const int lane = threadIdx.x & 31;
@@ -230,6 +242,8 @@ __global__ void __launch_bounds__(256) pack_bf16_kernel(const float* __restrict_
 
 __global__ void where_rows_kernel(float* __restrict__ x, long long ldx, const float* __restrict__ c, long long ldc,
                                   const int* __restrict__ flag, int M, int C) {
+  pdl_wait();
+  pdl_launch();
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= M || flag[row] == 0) return;
   for (int i = threadIdx.x & 31; i < C; i += 32) x[static_cast<size_t>(row) * ldx + i] = c[static_cast<size_t>(row) * ldc + i];
@@ -240,6 +254,8 @@ __global__ void __launch_bounds__(256) cfg_euler_kernel(float* __restrict__ x, l
                                                         long long ldp, int half_rows, int C, const int* __restrict__ row_pos,
                                                         const float* __restrict__ dts, int step, float cfg,
                                                         __nv_bfloat16* __restrict__ xb, long long ldxb, int C_pad) {
+  pdl_wait();
+  pdl_launch();
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= half_rows) return;
   const int lane = threadIdx.x & 31;
@@ -295,6 +311,8 @@ __device__ __forceinline__ float2 box_muller(uint32_t a, uint32_t b) {
 __global__ void __launch_bounds__(256) randn_rows_kernel(float* __restrict__ x, long long ldx, int M, int C,
                                                          const int* __restrict__ row_pos, const int* __restrict__ row_utt,
                                                          const unsigned long long* __restrict__ utt_seed) {
+  pdl_wait();
+  pdl_launch();
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= M) return;
   const int lane = threadIdx.x & 31;
@@ -319,6 +337,8 @@ __global__ void __launch_bounds__(256) randn_rows_kernel(float* __restrict__ x, 
 
 __global__ void time_sinus_kernel(const float* __restrict__ t, int steps, const float* __restrict__ freqs, int dim,
                                   __nv_bfloat16* __restrict__ out, long long ldo) {
+  pdl_wait();
+  pdl_launch();
   const int s = blockIdx.x;
   const int half = dim / 2;
   for (int k = threadIdx.x; k < half; k += blockDim.x) {
@@ -329,6 +349,8 @@ __global__ void time_sinus_kernel(const float* __restrict__ t, int steps, const 
 }
 
 __global__ void silu_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, long long n) {
+  pdl_wait();
+  pdl_launch();
   const long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 2;
   if (i + 1 < n) {
     const float2 v = *reinterpret_cast<const float2*>(x + i);
@@ -351,7 +373,7 @@ extern "C" int f5_layernorm_mod(const float* x, int64_t ldx, void* y, int64_t ld
   const int grid = (M + 7) / 8;
   __nv_bfloat16* yo = reinterpret_cast<__nv_bfloat16*>(y);
   switch (D / 128) {
-#define F5_CASE(NV) case NV: layernorm_mod_kernel<NV><<<grid, 256, 0, F5_STREAM(stream)>>>(x, ldx, yo, ldy, y32, ldy32, M, a, b, a_off, eps); break;
+#define F5_CASE(NV) case NV: f5_launch(layernorm_mod_kernel<NV>, dim3(grid), dim3(256), 0, F5_STREAM(stream), x, ldx, yo, ldy, y32, ldy32, M, a, b, a_off, eps); break;
     F5_CASE(1) F5_CASE(2) F5_CASE(3) F5_CASE(4) F5_CASE(5) F5_CASE(6) F5_CASE(7) F5_CASE(8)
 #undef F5_CASE
   }
@@ -367,7 +389,7 @@ extern "C" int f5_dwconv7_ln(const float* x, int64_t ldx, void* y, int64_t ldy, 
   const int grid = blocks < kNumSMsB200 * 8 ? blocks : kNumSMsB200 * 8;
   __nv_bfloat16* yo = reinterpret_cast<__nv_bfloat16*>(y);
   switch (C / 128) {
-#define F5_CASE(NV) case NV: dwconv7_ln_kernel<NV><<<grid, 256, 0, F5_STREAM(stream)>>>(x, ldx, yo, ldy, M, row_pos, w, bias, ln_w, ln_b, eps); break;
+#define F5_CASE(NV) case NV: f5_launch(dwconv7_ln_kernel<NV>, dim3(grid), dim3(256), 0, F5_STREAM(stream), x, ldx, yo, ldy, M, row_pos, w, bias, ln_w, ln_b, eps); break;
     F5_CASE(1) F5_CASE(2) F5_CASE(3) F5_CASE(4)
 #undef F5_CASE
   }
@@ -380,7 +402,7 @@ extern "C" int f5_grn_sumsq(const void* x, int64_t ldx, int32_t C, const int32_t
                             void* stream) {
   if (!x || !seg_rows || !sumsq || num_segs <= 0 || C % 2 != 0 || ldx % 2 != 0) return F5_ERR_ARG;
   dim3 grid((C + 127) / 128, num_segs);
-  grn_sumsq_kernel<<<grid, 256, 0, F5_STREAM(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(x), ldx, C, seg_rows, sumsq);
+  f5_launch(grn_sumsq_kernel, dim3(grid), dim3(256), 0, F5_STREAM(stream), reinterpret_cast<const __nv_bfloat16*>(x), ldx, C, seg_rows, sumsq);
   return F5_LAUNCH_RC();
 }
 
@@ -388,21 +410,21 @@ extern "C" int f5_grn_apply(void* x, int64_t ldx, int32_t C, const int32_t* seg_
                             const float* gamma, const float* beta, void* stream) {
   if (!x || !seg_rows || !sumsq || !gamma || !beta || num_segs <= 0 || C % 2 != 0 || ldx % 2 != 0) return F5_ERR_ARG;
   dim3 grid((max_seg_rows_hint + GRN_ROWS - 1) / GRN_ROWS, num_segs);
-  grn_apply_kernel<<<grid, 256, 0, F5_STREAM(stream)>>>(reinterpret_cast<__nv_bfloat16*>(x), ldx, C, seg_rows, sumsq, gamma, beta);
+  f5_launch(grn_apply_kernel, dim3(grid), dim3(256), 0, F5_STREAM(stream), reinterpret_cast<__nv_bfloat16*>(x), ldx, C, seg_rows, sumsq, gamma, beta);
   return F5_LAUNCH_RC();
 }
 
 extern "C" int f5_text_gather_pos(const int32_t* ids, const int32_t* row_pos, const float* emb, const float* pos_table,
                                   int32_t max_pos, float* out, int64_t ldo, int32_t M, int32_t C, void* stream) {
   if (!ids || !row_pos || !emb || !pos_table || !out || M <= 0 || C % 4 != 0 || ldo % 4 != 0) return F5_ERR_ARG;
-  text_gather_pos_kernel<<<M, 128, 0, F5_STREAM(stream)>>>(ids, row_pos, emb, pos_table, max_pos, out, ldo, M, C);
+  f5_launch(text_gather_pos_kernel, dim3(M), dim3(128), 0, F5_STREAM(stream), ids, row_pos, emb, pos_table, max_pos, out, ldo, M, C);
   return F5_LAUNCH_RC();
 }
 
 extern "C" int f5_pack_bf16(const float* src, int64_t lds, void* dst, int64_t ldd, int32_t dst_col, int32_t M, int32_t C,
                             int32_t C_pad, const int32_t* src_rows, const int32_t* row_pos, void* stream) {
   if (!src || !dst || M <= 0 || C <= 0 || C_pad < C || C_pad % 2 != 0 || dst_col % 2 != 0 || ldd % 2 != 0) return F5_ERR_ARG;
-  pack_bf16_kernel<<<(M + 7) / 8, 256, 0, F5_STREAM(stream)>>>(src, lds, reinterpret_cast<__nv_bfloat16*>(dst), ldd, dst_col,
+  f5_launch(pack_bf16_kernel, dim3((M + 7) / 8), dim3(256), 0, F5_STREAM(stream), src, lds, reinterpret_cast<__nv_bfloat16*>(dst), ldd, dst_col,
                                                                M, C, C_pad, src_rows, row_pos);
   return F5_LAUNCH_RC();
 }
@@ -410,7 +432,7 @@ extern "C" int f5_pack_bf16(const float* src, int64_t lds, void* dst, int64_t ld
 extern "C" int f5_where_rows(float* x, int64_t ldx, const float* c, int64_t ldc, const int32_t* flag, int32_t M, int32_t C,
                              void* stream) {
   if (!x || !c || !flag || M <= 0 || C <= 0) return F5_ERR_ARG;
-  where_rows_kernel<<<(M + 7) / 8, 256, 0, F5_STREAM(stream)>>>(x, ldx, c, ldc, flag, M, C);
+  f5_launch(where_rows_kernel, dim3((M + 7) / 8), dim3(256), 0, F5_STREAM(stream), x, ldx, c, ldc, flag, M, C);
   return F5_LAUNCH_RC();
 }
 
@@ -419,7 +441,7 @@ extern "C" int f5_cfg_euler(float* x, int64_t ldx, const float* pred, int64_t ld
                             int64_t ldxb, int32_t C_pad, void* stream) {
   if (!x || !pred || !row_pos || !dts || !xb || half_rows <= 0 || C <= 0 || C_pad < C || C_pad % 2 != 0 || ldxb % 2 != 0)
     return F5_ERR_ARG;
-  cfg_euler_kernel<<<(half_rows + 7) / 8, 256, 0, F5_STREAM(stream)>>>(x, ldx, pred, ldp, half_rows, C, row_pos, dts, step,
+  f5_launch(cfg_euler_kernel, dim3((half_rows + 7) / 8), dim3(256), 0, F5_STREAM(stream), x, ldx, pred, ldp, half_rows, C, row_pos, dts, step,
                                                                        cfg_strength, reinterpret_cast<__nv_bfloat16*>(xb),
                                                                        ldxb, C_pad);
   return F5_LAUNCH_RC();
@@ -428,7 +450,7 @@ extern "C" int f5_cfg_euler(float* x, int64_t ldx, const float* pred, int64_t ld
 extern "C" int f5_randn_rows(float* x, int64_t ldx, int32_t M, int32_t C, const int32_t* row_pos, const int32_t* row_utt,
                              const uint64_t* utt_seed, void* stream) {
   if (!x || !row_pos || !row_utt || !utt_seed || M <= 0 || C <= 0 || C > 128 || ldx % 4 != 0) return F5_ERR_ARG;
-  randn_rows_kernel<<<(M + 7) / 8, 256, 0, F5_STREAM(stream)>>>(x, ldx, M, C, row_pos, row_utt,
+  f5_launch(randn_rows_kernel, dim3((M + 7) / 8), dim3(256), 0, F5_STREAM(stream), x, ldx, M, C, row_pos, row_utt,
                                                                 reinterpret_cast<const unsigned long long*>(utt_seed));
   return F5_LAUNCH_RC();
 }
@@ -436,14 +458,14 @@ extern "C" int f5_randn_rows(float* x, int64_t ldx, int32_t M, int32_t C, const 
 extern "C" int f5_time_sinus(const float* t, int32_t steps, const float* freqs, int32_t dim, void* out, int64_t ldo,
                              void* stream) {
   if (!t || !freqs || !out || steps <= 0 || dim <= 0 || dim % 2 != 0) return F5_ERR_ARG;
-  time_sinus_kernel<<<steps, 128, 0, F5_STREAM(stream)>>>(t, steps, freqs, dim, reinterpret_cast<__nv_bfloat16*>(out), ldo);
+  f5_launch(time_sinus_kernel, dim3(steps), dim3(128), 0, F5_STREAM(stream), t, steps, freqs, dim, reinterpret_cast<__nv_bfloat16*>(out), ldo);
   return F5_LAUNCH_RC();
 }
 
 extern "C" int f5_silu_bf16(const float* x, void* out, int64_t n, void* stream) {
   if (!x || !out || n <= 0) return F5_ERR_ARG;
   const long long pairs = (n + 1) / 2;
-  silu_bf16_kernel<<<static_cast<unsigned>((pairs + 255) / 256), 256, 0, F5_STREAM(stream)>>>(
+  f5_launch(silu_bf16_kernel, dim3(static_cast<unsigned>((pairs + 255) / 256)), dim3(256), 0, F5_STREAM(stream), 
       x, reinterpret_cast<__nv_bfloat16*>(out), n);
   return F5_LAUNCH_RC();
 }

@@ -39,6 +39,15 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// ------------------------------------------------------------------ programmatic dependent launch (PDL)
+// Every kernel of this library is launched with cudaLaunchAttributeProgrammaticStreamSerialization (f5_launch below) and calls
+// pdl_wait() before it touches global memory a predecessor may have written (or writes anything a predecessor may read), so its
+// set-up — barrier init, TMEM allocation, tensor-map prefetch, staging of weights — overlaps the tail of the previous kernel.
+// pdl_launch() right after it lets the NEXT kernel's CTAs be scheduled as soon as every CTA of this grid is under way.  The
+// single-request (B = 1) path is 5120 graph nodes of ~10 us each: the launch gap + prologue is a third of that.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ------------------------------------------------------------------ device-side fault record
 // One pointer per translation unit (no -rdc): set by f5_diag_enable() through the F5_DEFINE_DIAG_SETTER each .cu defines.
 // The record is ONE 16-byte store (any timed-out thread's record is a valid one; they are all stuck on the same pipeline):
@@ -176,7 +185,11 @@ __device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, b
       long long now;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
       if (t0 == 0) t0 = now;
-      if (now - t0 > F5_WATCHDOG_NS) diag_report_and_trap(addr, parity, now - t0);
+      // No record from here, and twice the limit: these waits are inlined ~45 times into the attention kernel's MMA / producer
+      // loops, and the record's instructions at every site cost 5 % of that kernel (instruction-cache footprint of a loop one
+      // sub-partition shares with two softmax warps).  A stuck pipeline stalls every role of the CTA within microseconds, so
+      // the per-thread waits of the softmax / epilogue warps (mbar_wait, mbar_wait_a) time out first and leave the record.
+      if (now - t0 > 2 * F5_WATCHDOG_NS) __trap();
     }
   }
 #endif
@@ -481,4 +494,23 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+}  // namespace f5
+
+// ------------------------------------------------------------------ host: launch with the PDL attribute
+extern int f5_pdl_enabled;   // gemm_tcgen05.cu; f5_set_pdl()
+namespace f5 {
+template <typename... KArgs, typename... Args>
+inline cudaError_t f5_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = f5_pdl_enabled ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 }  // namespace f5

@@ -120,6 +120,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   if (CL > 1) cluster_sync_all();            // the peer's barriers are initialised before anything can arrive on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();                                // everything above overlapped the previous kernel's tail; operands are read below
+  pdl_launch();
 
   constexpr int EPI_W0 = EW == 8 ? 4 : 2;    // first epilogue warp
   if (warp < EPI_W0) {
@@ -530,18 +532,28 @@ int launch_gemm(const f5_gemm_args& a, const GemmParams& p, cudaStream_t stream)
   cfg.blockDim = dim3((EW == 8 ? 12 : 6) * 32);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CL;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (CL > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = CL;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (f5_pdl_enabled) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = CL > 1 ? 1 : 0;
+  cfg.numAttrs = na;
   int max_walkers = sms / CL;
   if (CL > 1) {        // persistent kernel: no more clusters than the device can hold at once (a GPC with an odd SM count strands one)
     static const int max_clusters = [&] {
       cudaLaunchConfig_t q = cfg;
       q.gridDim = dim3(kNumSMsB200);
+      q.numAttrs = 1;                        // the cluster attribute only
       int n = 0;
       if (cudaOccupancyMaxActiveClusters(&n, gemm_tcgen05_kernel<BLOCK_N, ACT, CL, EW>, &q) != cudaSuccess || n <= 0) n = kNumSMsB200 / CL;
       return n;
@@ -554,6 +566,16 @@ int launch_gemm(const f5_gemm_args& a, const GemmParams& p, cudaStream_t stream)
 }
 
 }  // namespace f5
+
+int f5_pdl_enabled = [] { const char* e = getenv("F5_PDL"); return (e == nullptr || e[0] != '0') ? 1 : 0; }();
+
+// Programmatic dependent launch for every kernel of the library (default on; F5_PDL=0 in the environment or f5_set_pdl(0)
+// switches it off: A/B measurements).  Returns the previous setting.
+extern "C" int f5_set_pdl(int enabled) {
+  const int old = f5_pdl_enabled;
+  f5_pdl_enabled = enabled ? 1 : 0;
+  return old;
+}
 
 F5_DEFINE_DIAG_SETTER(f5_diag_set_gemm)
 int f5_diag_set_attn(void* mapped);   // attn_tcgen05.cu

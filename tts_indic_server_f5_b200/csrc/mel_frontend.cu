@@ -18,6 +18,8 @@ __global__ void __launch_bounds__(256) mel_frames_kernel(const float* __restrict
                                                          const float* __restrict__ window, const float* __restrict__ fbank,
                                                          const int* __restrict__ band, int n_mels, float* __restrict__ mel,
                                                          long long ldm) {
+  pdl_wait();
+  pdl_launch();
   __shared__ float2 buf[MEL_NFFT];
   __shared__ float2 tw[MEL_NFFT / 2];
   __shared__ float mag[MEL_BINS + 3];
@@ -72,6 +74,6 @@ extern "C" int f5_mel_frames(const float* wave, const int32_t* seg, int32_t num_
   if (wave == nullptr || seg == nullptr || window == nullptr || fbank == nullptr || band == nullptr || mel == nullptr) return F5_ERR_ARG;
   if (num_segs <= 0 || max_frames <= 0 || n_mels <= 0 || n_mels > 1024 || ldm < n_mels) return F5_ERR_ARG;
   dim3 grid(max_frames, num_segs);
-  mel_frames_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(wave, seg, window, fbank, band, n_mels, mel, ldm);
+  f5_launch(mel_frames_kernel, dim3(grid), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), wave, seg, window, fbank, band, n_mels, mel, ldm);
   return static_cast<int>(cudaGetLastError());
 }

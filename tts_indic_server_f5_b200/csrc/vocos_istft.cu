@@ -61,6 +61,8 @@ __device__ __forceinline__ void idft32_regs(float2 (&v)[32]) {
 constexpr int ISTFT_WARPS = 4;
 __global__ void __launch_bounds__(ISTFT_WARPS * 32) istft_frames_kernel(const float* __restrict__ spec, long long lds, int rows,
                                                                        const float* __restrict__ window, float* __restrict__ frames) {
+  pdl_wait();
+  pdl_launch();
   __shared__ float tre[ISTFT_WARPS][32][33];
   __shared__ float tim[ISTFT_WARPS][32][33];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -123,6 +125,8 @@ __global__ void __launch_bounds__(ISTFT_WARPS * 32) istft_frames_kernel(const fl
 __global__ void __launch_bounds__(256) istft_ola_kernel(const float* __restrict__ frames, const float* __restrict__ window,
                                                         const int* __restrict__ seg, float* __restrict__ wav,
                                                         const float* __restrict__ gains) {
+  pdl_wait();
+  pdl_launch();
   const int4 sg = *reinterpret_cast<const int4*>(seg + 4 * blockIdx.y);
   const int T = sg.y;
   const int len = HOP * (T - 1);
@@ -152,7 +156,7 @@ extern "C" int f5_istft_frames(const float* spec, int64_t lds, int32_t rows, con
   if (!spec || !window || !frames_out || rows <= 0 || lds < 2 * f5::NBINS) return F5_ERR_ARG;
   const int blocks = (rows + f5::ISTFT_WARPS - 1) / f5::ISTFT_WARPS;
   const int grid = blocks < 148 * 6 ? blocks : 148 * 6;
-  f5::istft_frames_kernel<<<grid, f5::ISTFT_WARPS * 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(spec, lds, rows, window, frames_out);
+  f5::f5_launch(f5::istft_frames_kernel, dim3(grid), dim3(f5::ISTFT_WARPS * 32), 0, reinterpret_cast<cudaStream_t>(stream), spec, lds, rows, window, frames_out);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -160,6 +164,6 @@ extern "C" int f5_istft_ola(const float* frames, const float* window, const int3
                             int32_t max_wav_len, float* wav, const float* gains, void* stream) {
   if (!frames || !window || !seg || !wav || num_segs <= 0 || max_wav_len <= 0) return F5_ERR_ARG;
   dim3 grid((max_wav_len + 255) / 256, num_segs);
-  f5::istft_ola_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(frames, window, seg, wav, gains);
+  f5::f5_launch(f5::istft_ola_kernel, dim3(grid), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), frames, window, seg, wav, gains);
   return static_cast<int>(cudaGetLastError());
 }
