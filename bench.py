@@ -195,6 +195,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"],
+                    help="fp32: split-operand GEMMs + fp32 attention (reported beside the headline, never instead of it)")
     ap.add_argument("--cpu-nfe", type=int, default=1, help="Euler steps per bounded CPU step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary blocks (C1 latency, C3, C5, torch-eager baseline)")
@@ -239,8 +241,8 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     _lib.enable_diag()
 
-    model = api.load_model(state_dict=W.make_dit_state_dict(W.INDICF5, seed=0), device=dev)
-    voc = api.load_vocoder(state_dict=W.make_vocos_state_dict(W.VOCOS_24K, seed=0), device=dev)
+    model = api.load_model(state_dict=W.make_dit_state_dict(W.INDICF5, seed=0), device=dev, precision=args.precision)
+    voc = api.load_vocoder(state_dict=W.make_vocos_state_dict(W.VOCOS_24K, seed=0), device=dev, precision=args.precision)
     model.engine.max_workspaces = 8
     syn = api.Synthesizer(model, voc)
     syn.prompt_cache.capacity = 0      # every step is a fresh request: prompt audio H2D + prompt mel are redone each time
@@ -353,6 +355,8 @@ def main():
     finally:
         eng.use_graphs, ops.gemm, ops.attention = True, orig_gemm, orig_attn
     real_rows = 2 * st.layout.real_tokens                      # CFG pair; gap rows are not algorithmic work
+    if args.precision == "fp32":             # split-operand launches: B holds three row-stacked planes, three products per k-block
+        recs = [(M, N // 3 if taps == 1 else N, K, taps, a, b) for (M, N, K, taps, a, b) in recs]
     layer = [(N, K, a.elapsed_time(b) * 1e-3) for (M, N, K, taps, a, b) in recs if taps == 1 and N % 256 == 0 and K >= 1024]
     g_flops = sum(2.0 * real_rows * N * K for N, K, _ in layer)
     g_time = sum(t for _, _, t in layer)
@@ -441,7 +445,8 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": args.scaling if world > 1 else "weak",
-            "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "restarts": 0,
+            "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "fp32x3 (hi+lo bf16 operand planes, fp32 attention)",
+            "data": "synthetic", "restarts": 0,
             "config": {"workload": describe(wl_name, all_specs), "utterances": len(all_specs),
                        "utterances_per_gpu": [len(p) for p in plan["parts"]], "packs_per_gpu": npk,
                        "lpt_imbalance": plan["imbalance"], "tokens_rank0": sum(s.duration for s in mine),

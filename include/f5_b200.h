@@ -65,6 +65,15 @@ typedef struct f5_gemm_args {
   int32_t rope_period;          /* RoPE applies to columns [t*period, t*period+64), t < rope_tiles     */
   int32_t rope_tiles;
   int32_t num_sms;              /* persistent grid size (0 => 148)                                     */
+  /* Split-operand ("bf16x3") mode — fp32-class products on the bf16 tensor cores for the fp32 precision mode (the reference as
+   * deployed is fp32 end to end, core/managers.py:76): every operand is carried as two bf16 planes, v = hi + lo with
+   * hi = bf16(v), lo = bf16(v - hi), and D = A_hi B_hi^T + A_hi B_lo^T + A_lo B_hi^T (the lo x lo term is below fp32 round-off of
+   * the sum).  taps_per_seg > 0 switches it on: num_taps must be 3 * taps_per_seg; tap = seg * taps_per_seg + t shifts the A rows
+   * by (t - tap_pad) as usual; B holds the planes stacked by rows in the order [hi taps | lo taps | hi taps] (b_tap_rows rows per
+   * tap); A holds its low plane a_lo_off columns (a multiple of 64) to the right of the high plane and segment 2 reads it.
+   * taps_per_seg == 0: ordinary launch.                                                                       */
+  int32_t taps_per_seg;
+  int32_t a_lo_off;
 } f5_gemm_args;
 
 int f5_gemm_bf16(const f5_gemm_args* args, void* stream);
@@ -79,16 +88,29 @@ int f5_attention_d64(const void* qkv, int64_t ld, int32_t rows, int32_t q_col, i
                      int32_t heads, const int32_t* tiles, int32_t num_tiles, void* out, int64_t ldo,
                      float softmax_scale, void* stream);
 
+/* fp32 attention for the fp32 precision mode: same work items and per-utterance semantics as f5_attention_d64, but Q / K / V are
+ * fp32 (the QKV GEMM's fp32 output), every product, the softmax and the accumulation are fp32 on the CUDA cores, and RoPE
+ * (x-transformers rotary on head 0 only, model/modules.py:414-426) is applied while Q and K are loaded: rope fp32 [max_pos, 64] =
+ * (cos, sin) per interleaved pair, NULL = none.  out: bf16 [rows, ldo] with head h at h*64; lo_off > 0 writes the split planes.
+ * Replaces F.scaled_dot_product_attention at model/modules.py:436 in fp32. */
+int f5_attention_f32(const float* qkv, int64_t ld, int32_t q_col, int32_t k_col, int32_t v_col, int32_t heads,
+                     const int32_t* tiles, int32_t num_tiles, const float* rope, void* out, int64_t ldo, int32_t lo_off,
+                     float softmax_scale, void* stream);
+
 /* y[m,:] = LayerNorm(x_f32[m,:], eps) * (a_off + a[:]) + b[:] (bf16 and/or fp32 output, either may be NULL) — model/modules.py:289,:310,:568 (a_off = 1,
  * a = scale, b = shift) and the affine LayerNorms of ConvNeXtV2 / Vocos (a_off = 0, a = weight, b = bias).  D % 128 == 0, D <= 1024. */
 int f5_layernorm_mod(const float* x, int64_t ldx, void* y_bf16, int64_t ldy, float* y_f32, int64_t ldy32, int32_t M,
-                     int32_t D, const float* a, const float* b, float a_off, float eps, void* stream);
+                     int32_t D, const float* a, const float* b, float a_off, float eps, int32_t lo_off, void* stream);
+
+/* Split-operand outputs (fp32 precision mode).  Kernels that produce a bf16 GEMM operand take `lo_off`: 0 = the ordinary bf16
+ * output; > 0 = the value v is written as two planes, hi = bf16(v) at the usual column and lo = bf16(v - hi) lo_off columns to the
+ * right (the A operand layout of f5_gemm_bf16's split-operand mode). */
 
 /* Depthwise Conv1d(k=7, pad=3) over the rows of one utterance + affine LayerNorm -> bf16
  * (model/modules.py:262-264; Vocos ConvNeXtBlock).  row_pos marks utterance membership (halo rows with row_pos < 0 or
  * outside [0,M) contribute zero).  w: fp32 [C,7], bias [C]. */
 int f5_dwconv7_ln(const float* x, int64_t ldx, void* y, int64_t ldy, int32_t M, int32_t C, const int32_t* row_pos,
-                  const float* w, const float* bias, const float* ln_w, const float* ln_b, float eps, void* stream);
+                  const float* w, const float* bias, const float* ln_w, const float* ln_b, float eps, int32_t lo_off, void* stream);
 
 /* GRN over each utterance's own rows (model/modules.py:231-234): phase 1 computes the sum of squares per (segment,
  * channel) in a fixed order (deterministic, no atomics); phase 2 applies gamma*(x*Nx)+beta+x in place on the bf16 activations. */
@@ -96,6 +118,10 @@ int f5_grn_sumsq(const void* x_bf16, int64_t ldx, int32_t C, const int32_t* seg_
                  void* stream);
 int f5_grn_apply(void* x_bf16, int64_t ldx, int32_t C, const int32_t* seg_rows, int32_t num_segs, const float* sumsq,
                  const float* gamma, const float* beta, void* stream);
+/* The same two passes on fp32 activations (fp32 precision mode). */
+int f5_grn_sumsq_f32(const float* x, int64_t ldx, int32_t C, const int32_t* seg_rows, int32_t num_segs, float* sumsq, void* stream);
+int f5_grn_apply_f32(float* x, int64_t ldx, int32_t C, const int32_t* seg_rows, int32_t num_segs, const float* sumsq,
+                     const float* gamma, const float* beta, void* stream);
 
 /* Text token gather + absolute sinusoidal position (model/backbones/dit.py:56-64): out_f32[row,:] = emb[ids[row]] +
  * pos_table[min(row_pos[row], max_pos-1)] for rows with row_pos >= 0, zeros otherwise. */
@@ -105,7 +131,7 @@ int f5_text_gather_pos(const int32_t* ids, const int32_t* row_pos, const float* 
 /* fp32 -> bf16 row gather/pack into a GEMM A operand: dst[m, dst_col + c] = src[src_rows ? src_rows[m] : m, c] for
  * c < C, zero fill for C <= c < C_pad; rows whose source index (or row_pos[m], when given) is negative are zeros. */
 int f5_pack_bf16(const float* src, int64_t lds, void* dst, int64_t ldd, int32_t dst_col, int32_t M, int32_t C,
-                 int32_t C_pad, const int32_t* src_rows, const int32_t* row_pos, void* stream);
+                 int32_t C_pad, const int32_t* src_rows, const int32_t* row_pos, int32_t lo_off, void* stream);
 
 /* x[m,:] = flag[m] ? c[m,:] : x[m,:]   — prompt re-insert `where(cond_mask, cond, out)` (model/cfm.py:204). */
 int f5_where_rows(float* x, int64_t ldx, const float* c, int64_t ldc, const int32_t* flag, int32_t M, int32_t C,
@@ -129,10 +155,11 @@ int f5_randn_rows(float* x, int64_t ldx, int32_t M, int32_t C, const int32_t* ro
 /* Sinusoidal time embedding (model/modules.py:154-160): out_bf16[s, :] = [sin((1000 t_s) f_k) | cos(...)], k < dim/2;
  * freqs = exp(-k ln(1e4)/(dim/2-1)) is passed in (fp32 [dim/2]). */
 int f5_time_sinus(const float* t, int32_t steps, const float* freqs, int32_t dim, void* out_bf16, int64_t ldo,
-                  void* stream);
+                  int32_t lo_off, void* stream);
 
-/* out_bf16 = silu(x_f32) elementwise (AdaLN input, model/modules.py:286). */
-int f5_silu_bf16(const float* x, void* out_bf16, int64_t n, void* stream);
+/* out_bf16 = silu(x_f32) elementwise (AdaLN input, model/modules.py:286).  split_cols > 0: x is [n / split_cols, split_cols] and
+ * out is [rows, 2 * split_cols] = high plane | low plane (fp32 precision mode). */
+int f5_silu_bf16(const float* x, void* out_bf16, int64_t n, int32_t split_cols, void* stream);
 
 /* Vocos ISTFT head (vocos 0.1.0 ISTFTHead, call site infer/utils_infer.py:472): per frame mag = min(exp(m), 1e2),
  * S = mag (cos p + i sin p); irfft(1024) * hann; overlap-add with hop 256; divide by the window envelope; trim

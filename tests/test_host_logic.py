@@ -194,7 +194,10 @@ def test_launchers_reject_bad_arguments_without_touching_the_gpu():
     assert _lib.lib.f5_gemm_bf16(ctypes.byref(a), None) == -1            # F5_ERR_ARG: null operands
     a.A, a.B, a.M, a.N, a.num_taps, a.kc_per_tap, a.block_n = 1 << 20, 1 << 21, 128, 100, 1, 1, 256
     assert _lib.lib.f5_gemm_bf16(ctypes.byref(a), None) == -1            # N % 8 != 0
-    assert _lib.lib.f5_layernorm_mod(None, 0, None, 0, None, 0, 1, 128, None, None, 1.0, 1e-6, None) == -1
+    assert _lib.lib.f5_layernorm_mod(None, 0, None, 0, None, 0, 1, 128, None, None, 1.0, 1e-6, 0, None) == -1
+    assert _lib.lib.f5_attention_f32(None, 0, 0, 0, 0, 16, None, 0, None, None, 0, 0, 0.125, None) == -1
+    a.taps_per_seg, a.num_taps, a.N = 2, 3, 128                            # split-operand mode needs num_taps == 3 * taps_per_seg
+    assert _lib.lib.f5_gemm_bf16(ctypes.byref(a), None) == -1
     assert _lib.lib.f5_attention_d64(None, 0, 0, 0, 0, 0, 16, None, 0, None, 0, 0.125, None) == -1
     with pytest.raises(_lib.F5Error):
         _lib.check(-2, "x")

@@ -486,3 +486,115 @@ def test_randn_rows_vs_philox_oracle():
     ops.randn_rows(big[:Lb.half_rows], 100, Lb.row_pos[:Lb.half_rows].to(DEV), Lb.row_utt.to(DEV), sd[:1].contiguous())
     z = big[Lb.starts[0]:Lb.starts[0] + 4096, :100]
     assert abs(float(z.mean())) < 5e-3 and abs(float(z.std()) - 1) < 5e-3 and float(z.abs().max()) < 6.0
+
+
+# ------------------------------------------------------------------------------------------------ round 2: fp32 precision mode
+def _planes(x, lo_first_col):
+    """fp32 [M, K] -> bf16 [M, 2K] = hi | lo through the product's own splitter (f5_pack_bf16 with lo_off)."""
+    M, K = x.shape
+    out = torch.zeros(M, 2 * K, device=DEV, dtype=torch.bfloat16)
+    ops.pack_bf16(x.contiguous(), out, 0, K, K, lo_off=lo_first_col)
+    return out
+
+
+def test_split_planes_reconstruct_the_value():
+    """hi + lo carries 16 mantissa bits: |v - (hi + lo)| <= 2^-17 |v| (pack, LayerNorm and silu writers)."""
+    from tts_indic_server_f5_b200.engine import split_planes
+    x = rnd(257, 384, seed=70, scale=3.0)
+    p = _planes(x, 384).float()
+    rec = p[:, :384] + p[:, 384:]
+    assert ((rec - x).abs() <= x.abs() * 2.0 ** -16 + 1e-30).all()
+    w3 = split_planes(x.cpu())
+    assert torch.equal(w3[:257], w3[514:]) and ((w3[:257].float() + w3[257:514].float() - x.cpu()).abs() <= x.cpu().abs() * 2.0 ** -16).all()
+    a, b = rnd(384, seed=71), rnd(384, seed=72)
+    y = torch.zeros(257, 768, device=DEV, dtype=torch.bfloat16)
+    y32 = torch.zeros(257, 384, device=DEV)
+    ops.layernorm_mod(x, y, a, b, 1.0, y32=y32, lo_off=384)
+    rec = y[:, :384].float() + y[:, 384:].float()
+    assert ((rec - y32).abs() <= y32.abs() * 2.0 ** -16 + 1e-30).all()
+    s_out = torch.zeros(257, 768, device=DEV, dtype=torch.bfloat16)
+    ops.silu_bf16(x, s_out, split=True)
+    rec = s_out[:, :384].float() + s_out[:, 384:].float()
+    ref = F.silu(x)
+    assert ((rec - ref).abs() <= ref.abs() * 2.0 ** -15 + 1e-6).all()
+
+
+@pytest.mark.parametrize("M,N,K,mode", [(300, 256, 128, "f32"), (1000, 3072, 1024, "f32"), (515, 1024, 2048, "resid"), (257, 104, 640, "f32")])
+def test_gemm_split_operand_is_fp32_class(M, N, K, mode):
+    """D = A_hi B_hi^T + A_hi B_lo^T + A_lo B_hi^T against a float64 product of the SAME fp32 operands: rel-L2 <= 2e-5
+    (the plain bf16-operand GEMM sits at ~3e-3 on these inputs)."""
+    from tts_indic_server_f5_b200.engine import split_planes
+    A, W = rnd(M, K, seed=80), rnd(N, K, seed=81, scale=1 / math.sqrt(K))
+    bias = rnd(N, seed=82)
+    Ap, W3 = _planes(A, K), split_planes(W.cpu()).to(DEV)
+    ref = (A.double() @ W.double().t() + bias.double())
+    if mode == "f32":
+        out = torch.zeros(M, N, device=DEV)
+        ops.gemm(Ap, W3, mode=ops.F5_EPI_STORE_F32, bias=bias, out=out, split=True)
+    else:
+        gate, x0 = rnd(N, seed=83), rnd(M, N, seed=84)
+        out = x0.clone()
+        ops.gemm(Ap, W3, mode=ops.F5_EPI_RESID_F32, bias=bias, gate=gate, resid=out, split=True)
+        ref = x0.double() + gate.double() * ref
+    torch.cuda.synchronize()
+    check(f"split gemm {M}x{N}x{K} {mode}", out, ref.float(), rel=2e-5)
+    plain = torch.zeros(M, N, device=DEV)
+    ops.gemm(A.to(torch.bfloat16), W.to(torch.bfloat16), mode=ops.F5_EPI_STORE_F32, bias=bias, out=plain)
+    if mode == "f32":
+        assert rel_err(plain, ref.float()) > 20 * rel_err(out, ref.float())
+
+
+def test_gemm_split_operand_grouped_conv31():
+    from tts_indic_server_f5_b200.engine import split_planes
+    C, G, Kw, n1, n2, gap = 256, 4, 31, 150, 230, 16
+    M = gap + n1 + gap + n2 + gap
+    x = torch.zeros(M, C, device=DEV)
+    x[gap:gap + n1] = rnd(n1, C, seed=16)
+    x[2 * gap + n1:2 * gap + n1 + n2] = rnd(n2, C, seed=17)
+    w = rnd(C, C // G, Kw, seed=18, scale=1 / math.sqrt(C // G * Kw))
+    bias = rnd(C, seed=19)
+    wt = w.permute(2, 0, 1).contiguous().reshape(Kw * C, C // G)                 # [tap][out][in], fp32
+    out = torch.zeros(M, C, device=DEV)
+    ops.gemm(_planes(x, C), split_planes(wt.cpu()).to(DEV), M=M, N=C, mode=ops.F5_EPI_STORE_F32, act=ops.F5_ACT_MISH, bias=bias, out=out,
+             block_n=64, num_taps=Kw, kc_per_tap=1, tap_pad=Kw // 2, a_grouped=True, b_tap_rows=C, split=True)
+    torch.cuda.synchronize()
+    for s0, n in ((gap, n1), (2 * gap + n1, n2)):
+        ref = F.mish(F.conv1d(x[s0:s0 + n].double().t()[None], w.double(), bias.double(), padding=Kw // 2, groups=G))[0].t()
+        check(f"split conv31 seg@{s0}", out[s0:s0 + n], ref.float(), rel=3e-5)
+
+
+def test_attention_f32_vs_sdpa():
+    """f5_attention_f32 against fp32 SDPA per utterance and head, with the x-transformers rotary embedding on head 0
+    (interleaved pairs, modules.py:414-426); output planes hi + lo reconstruct the fp32 result to 2^-16."""
+    from tts_indic_server_f5_b200.layout import build_layout
+    lens, H, D = [300, 77, 513, 128, 1], 4, 256
+    L = build_layout(lens)
+    qkv = rnd(L.rows, 3 * D, seed=90)
+    qkv[:, :D] *= 3.0                                                            # peaky rows exercise the running-max rescale
+    inv = 1.0 / (10000.0 ** (torch.arange(0, 64, 2).float() / 64))
+    ra = torch.arange(1024).float()[:, None] * inv[None]
+    rope = torch.stack((ra.cos(), ra.sin()), dim=-1).reshape(1024, 64).to(DEV)
+    out = torch.zeros(L.rows, 2 * D, device=DEV, dtype=torch.bfloat16)
+    ops.attention_f32(qkv, L.attn_tiles.to(DEV), out, H, 0, D, 2 * D, 0.125, rope=rope, lo_off=D)
+    torch.cuda.synchronize()
+    got = out[:, :D].float() + out[:, D:].float()
+
+    def rot(x, n):                                                               # x [n, 64]
+        c, s = ra[:n].cos().to(DEV), ra[:n].sin().to(DEV)
+        x0, x1 = x[:, 0::2], x[:, 1::2]
+        return torch.stack((x0 * c - x1 * s, x1 * c + x0 * s), dim=-1).reshape(n, 64)
+
+    worst = 0.0
+    for half in (0, L.half_rows):
+        for s0, n in zip(L.starts, lens):
+            blk = qkv[half + s0: half + s0 + n].double()
+            for h in range(H):
+                q, k, v = blk[:, h * 64:(h + 1) * 64], blk[:, D + h * 64:D + (h + 1) * 64], blk[:, 2 * D + h * 64:2 * D + (h + 1) * 64]
+                if h == 0:
+                    q, k = rot(q.float(), n).double(), rot(k.float(), n).double()
+                ref = torch.softmax(q @ k.t() * 0.125, dim=-1) @ v
+                worst = max(worst, float((got[half + s0: half + s0 + n, h * 64:(h + 1) * 64].double() - ref).abs().max()))
+    print(f"[attention_f32] max-abs {worst:.2e}")
+    assert worst < 2e-5
+    gaps = (L.row_pos < 0).to(DEV)
+    assert out[gaps].abs().max().item() == 0

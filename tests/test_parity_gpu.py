@@ -369,11 +369,12 @@ def test_tts_manager_load_and_synthesize_vs_oracle(tiny_models, tmp_path):
     assert len(chunks) >= 2
     vocab = {t: i for i, t in enumerate(T.synthetic_indic_vocab())}
     waves = []
+    rt2 = rt + " " if len(rt[-1].encode("utf-8")) == 1 else rt              # utils_infer.py:438-439 (inside infer_batch_process)
     with torch.inference_mode():
         for i, ch in enumerate(chunks):
             a, _ = O.rms_normalise(audio)
-            ids = O.list_str_to_idx(T.convert_char_to_pinyin([rt + ch]), vocab)
-            dur = O.estimate_duration(a.shape[-1] // 256, rt, ch)
+            ids = O.list_str_to_idx(T.convert_char_to_pinyin([rt2 + ch]), vocab)
+            dur = O.estimate_duration(a.shape[-1] // 256, rt2, ch)
             wv, _ = O.infer_one(sd, cfg, vsd, vcfg, audio, ids, dur, y0=S.initial_noise(4096, i))
             waves.append(wv.numpy())
     want = np.clip(O.cross_fade(waves) * 32768.0, -32768, 32767).astype(np.int16)
@@ -436,6 +437,7 @@ def test_programmatic_dependent_launch_is_bit_invisible(tiny_models):
     cfg, vcfg, sd, vsd, model, voc = tiny_models
     specs = S.workload("tiny3")
     m2 = api.load_model(state_dict=sd)                       # own engine: own workspaces and graphs
+    m2.engine.pdl_auto = False                               # this test drives the switch itself
     syn = api.Synthesizer(m2, voc)
     old = _lib.lib.f5_set_pdl(0)
     try:
@@ -450,3 +452,48 @@ def test_programmatic_dependent_launch_is_bit_invisible(tiny_models):
         _lib.lib.f5_set_pdl(old)
     for a, b, c, d in zip(off, on_eager, on_graph, on_replay):
         assert np.array_equal(a, b) and np.array_equal(a, c) and np.array_equal(a, d)
+
+
+# ------------------------------------------------------------------------------------------------ round 2: fp32 precision mode
+FP32_MEL_REL, FP32_MEL_LINF, FP32_WAVE_SNR = 5e-4, 5e-3, 60.0
+
+
+@pytest.fixture(scope="module")
+def tiny_models_fp32():
+    cfg, vcfg = W.tiny_dit_config(), W.tiny_vocos_config()
+    sd, vsd = W.make_dit_state_dict(cfg, seed=1), W.make_vocos_state_dict(vcfg, seed=1)
+    return api.load_model(state_dict=sd, precision="fp32"), api.load_vocoder(state_dict=vsd, precision="fp32")
+
+
+def test_fp32_mode_tiny_vs_reference_golden(tiny_models_fp32, golden_dir):
+    """precision="fp32" (split-operand GEMMs + fp32 attention) against the real reference's fp32 output — its own tolerance,
+    stated separately from the bf16 numbers: mel rel-L2 <= 5e-4, L-inf <= 5e-3, waveform SNR >= 60 dB."""
+    model, voc = tiny_models_fp32
+    g = np.load(os.path.join(golden_dir, "tiny.npz"))
+    u = UtteranceInput(cond=torch.from_numpy(g["fwd_condin"]), text_ids=torch.from_numpy(g["fwd_text"]), n=96, cond_len=96,
+                       y0=torch.from_numpy(g["fwd_x"]))
+    pc = model.engine.forward_flow([u], 0.37)[0].cpu().numpy()
+    print(f"fp32 forward pair: rel-L2 {rel(pc[0], g['fwd_cond']):.2e} / {rel(pc[1], g['fwd_null']):.2e}")
+    assert rel(pc[0], g["fwd_cond"]) < 1e-4 and rel(pc[1], g["fwd_null"]) < 1e-4
+    for wl in ("tiny", "tiny3"):
+        specs = S.workload(wl)
+        waves, mels = api.Synthesizer(model, voc).generate(specs, return_mel=True, y0=ref_noise(specs))
+        for i, (spec, wv, ml) in enumerate(zip(specs, waves, mels)):
+            gm = g[f"{wl}_{i}_mel"][spec.meta["ref_len"]:]
+            r, li, s = rel(ml.T, gm), float(np.abs(ml.T - gm).max()), snr(wv, g[f"{wl}_{i}_wave"])
+            print(f"fp32 {wl}[{i}] mel rel-L2 {r:.2e} L-inf {li:.4f} wave SNR {s:.1f} dB")
+            assert r < FP32_MEL_REL and li < FP32_MEL_LINF and s > FP32_WAVE_SNR
+
+
+def test_fp32_mode_full_size_c1_vs_reference_golden(golden_dir):
+    model = api.load_model(state_dict=W.make_dit_state_dict(W.INDICF5, seed=0), precision="fp32")
+    voc = api.load_vocoder(state_dict=W.make_vocos_state_dict(W.VOCOS_24K, seed=0), precision="fp32")
+    g = np.load(os.path.join(golden_dir, "full_c1.npz"))
+    spec = S.workload("c1")
+    waves, mels = api.Synthesizer(model, voc).generate(spec, return_mel=True, y0=ref_noise(spec))
+    gm = g["mel"][spec[0].meta["ref_len"]:]
+    r, li, s = rel(mels[0].T, gm), float(np.abs(mels[0].T - gm).max()), snr(waves[0], g["wave"])
+    print(f"fp32 full C1: mel rel-L2 {r:.2e} L-inf {li:.4f} wave SNR {s:.1f} dB")
+    assert r < FP32_MEL_REL and li < FP32_MEL_LINF and s > FP32_WAVE_SNR
+    del model, voc
+    torch.cuda.empty_cache()

@@ -16,7 +16,7 @@ F5_EPI_STORE_BF16, F5_EPI_STORE_F32, F5_EPI_RESID_F32 = 0, 1, 2
 F5_ACT_NONE, F5_ACT_GELU_TANH, F5_ACT_GELU_ERF, F5_ACT_MISH = 0, 1, 2, 3
 
 EXPORTS = [
-    "f5_gemm_bf16", "f5_attention_d64", "f5_layernorm_mod", "f5_dwconv7_ln", "f5_grn_sumsq", "f5_grn_apply",
+    "f5_gemm_bf16", "f5_attention_d64", "f5_attention_f32", "f5_grn_sumsq_f32", "f5_grn_apply_f32", "f5_layernorm_mod", "f5_dwconv7_ln", "f5_grn_sumsq", "f5_grn_apply",
     "f5_text_gather_pos", "f5_pack_bf16", "f5_where_rows", "f5_cfg_euler", "f5_time_sinus", "f5_silu_bf16",
     "f5_istft_frames", "f5_istft_ola", "f5_mel_frames", "f5_randn_rows", "f5_diag_enable", "f5_set_pdl", "f5_device_check", "f5_version",
 ]
@@ -36,6 +36,7 @@ class GemmArgs(C.Structure):
         ("addend", C.c_void_p), ("ld_add", C.c_int64), ("resid", C.c_void_p), ("ldr", C.c_int64),
         ("row_pos", C.c_void_p), ("mask_rows", C.c_int32),
         ("rope", C.c_void_p), ("rope_period", C.c_int32), ("rope_tiles", C.c_int32), ("num_sms", C.c_int32),
+        ("taps_per_seg", C.c_int32), ("a_lo_off", C.c_int32),
     ]
 
 
@@ -52,16 +53,19 @@ def _load() -> C.CDLL:
     sig = {
         "f5_gemm_bf16": [C.POINTER(GemmArgs), vp],
         "f5_attention_d64": [vp, i64, i32, i32, i32, i32, i32, vp, i32, vp, i64, f32, vp],
-        "f5_layernorm_mod": [vp, i64, vp, i64, vp, i64, i32, i32, vp, vp, f32, f32, vp],
-        "f5_dwconv7_ln": [vp, i64, vp, i64, i32, i32, vp, vp, vp, vp, vp, f32, vp],
+        "f5_attention_f32": [vp, i64, i32, i32, i32, i32, vp, i32, vp, vp, i64, i32, f32, vp],
+        "f5_layernorm_mod": [vp, i64, vp, i64, vp, i64, i32, i32, vp, vp, f32, f32, i32, vp],
+        "f5_dwconv7_ln": [vp, i64, vp, i64, i32, i32, vp, vp, vp, vp, vp, f32, i32, vp],
+        "f5_grn_sumsq_f32": [vp, i64, i32, vp, i32, vp, vp],
+        "f5_grn_apply_f32": [vp, i64, i32, vp, i32, vp, vp, vp, vp],
         "f5_grn_sumsq": [vp, i64, i32, vp, i32, vp, vp],
         "f5_grn_apply": [vp, i64, i32, vp, i32, vp, vp, vp, vp],
         "f5_text_gather_pos": [vp, vp, vp, vp, i32, vp, i64, i32, i32, vp],
-        "f5_pack_bf16": [vp, i64, vp, i64, i32, i32, i32, i32, vp, vp, vp],
+        "f5_pack_bf16": [vp, i64, vp, i64, i32, i32, i32, i32, vp, vp, i32, vp],
         "f5_where_rows": [vp, i64, vp, i64, vp, i32, i32, vp],
         "f5_cfg_euler": [vp, i64, vp, i64, i32, i32, vp, vp, i32, f32, vp, i64, i32, vp],
-        "f5_time_sinus": [vp, i32, vp, i32, vp, i64, vp],
-        "f5_silu_bf16": [vp, vp, i64, vp],
+        "f5_time_sinus": [vp, i32, vp, i32, vp, i64, i32, vp],
+        "f5_silu_bf16": [vp, vp, i64, i32, vp],
         "f5_istft_frames": [vp, i64, i32, vp, vp, vp],
         "f5_istft_ola": [vp, vp, vp, i32, i32, vp, vp, vp],
         "f5_mel_frames": [vp, vp, i32, i32, vp, vp, vp, i32, vp, i64, vp],

@@ -68,13 +68,14 @@ def utterance_seed(base: int, index: int) -> int:
 class CFM:
     """Engine-backed stand-in for the reference `CFM` (inference surface only: `.sample`, `.device`, `.eval`, `.to`)."""
 
-    def __init__(self, state_dict: dict, cfg: DiTConfig, vocab_char_map: dict | None = None, device: str = "cuda"):
+    def __init__(self, state_dict: dict, cfg: DiTConfig, vocab_char_map: dict | None = None, device: str = "cuda",
+                 precision: str = "bf16"):
         if not str(device).startswith("cuda"):
             raise RuntimeError("the B200 CFM engine runs on CUDA (sm_100a) only; there is no CPU fallback")
         self.cfg = cfg
         self.vocab_char_map = vocab_char_map
         self.num_channels = cfg.mel_dim
-        self.engine = F5Engine(state_dict, cfg, device)
+        self.engine = F5Engine(state_dict, cfg, device, precision=precision)
         self._device = self.engine.device
 
     @property
@@ -158,8 +159,8 @@ class CFM:
 class Vocos:
     """Engine-backed stand-in for `vocos.Vocos` (only `.decode` is used on the path, utils_infer.py:472)."""
 
-    def __init__(self, state_dict: dict, cfg: VocosConfig = VOCOS_24K, device: str = "cuda"):
-        self.engine = VocosEngine(state_dict, cfg, device)
+    def __init__(self, state_dict: dict, cfg: VocosConfig = VOCOS_24K, device: str = "cuda", precision: str = "bf16"):
+        self.engine = VocosEngine(state_dict, cfg, device, precision=precision)
         self.cfg = cfg
 
     def decode(self, mel: torch.Tensor) -> torch.Tensor:
@@ -173,7 +174,7 @@ class Vocos:
 
 
 def load_vocoder(vocoder_name="vocos", is_local=False, local_path="", device=None, hf_cache_dir=None, state_dict=None,
-                 seed: int = 0) -> Vocos:
+                 seed: int = 0, precision: str = "bf16") -> Vocos:
     """utils_infer.py:92-130.  `is_local`: reads `<local_path>/pytorch_model.bin` (vocos-mel-24khz layout).  Without
     local weights (no network here) a seeded random-init Vocos of the named architecture is built."""
     device = device or _default_device()
@@ -187,11 +188,12 @@ def load_vocoder(vocoder_name="vocos", is_local=False, local_path="", device=Non
     cfg = VocosConfig(dim=state_dict["backbone.embed.weight"].shape[0],
                       intermediate_dim=state_dict["backbone.convnext.0.pwconv1.weight"].shape[0],
                       num_layers=1 + max(int(k.split(".")[2]) for k in state_dict if k.startswith("backbone.convnext.")))
-    return Vocos(state_dict, cfg, device)
+    return Vocos(state_dict, cfg, device, precision=precision)
 
 
 def load_model(model_cls=None, model_cfg=None, mel_spec_type=mel_spec_type, vocab_file="", ode_method=ode_method,
-               use_ema=True, device=None, state_dict=None, ckpt_path: str | None = None, seed: int = 0) -> CFM:
+               use_ema=True, device=None, state_dict=None, ckpt_path: str | None = None, seed: int = 0,
+               precision: str = "bf16") -> CFM:
     """utils_infer.py:224-260.  Like the reference fork, no checkpoint is read unless one is given explicitly
     (`state_dict=` or `ckpt_path=`, EMA key rules of :195-213); otherwise weights are seeded random-init."""
     device = device or _default_device()
@@ -219,7 +221,7 @@ def load_model(model_cls=None, model_cfg=None, mel_spec_type=mel_spec_type, voca
                         ff_mult=kw.get("ff_mult", base.ff_mult), text_dim=kw.get("text_dim", base.text_dim),
                         conv_layers=kw.get("conv_layers", base.conv_layers), vocab_size=vocab_size)
         state_dict = make_dit_state_dict(cfg, seed=seed)
-    return CFM(state_dict, cfg, vocab_char_map, device)
+    return CFM(state_dict, cfg, vocab_char_map, device, precision=precision)
 
 
 def preprocess_ref_audio_text(ref_audio_orig, ref_text, clip_short=True, show_info=print, device=None):
@@ -460,12 +462,13 @@ class INF5Model:
 
     def __init__(self, vocab_file: str = "", device: str | None = None, ckpt_path: str | None = None,
                  vocoder_path: str = "", seed: int = 0, output_int16: bool = True, model_cfg: dict | None = None,
-                 state_dict: dict | None = None, vocoder_state_dict: dict | None = None):
+                 state_dict: dict | None = None, vocoder_state_dict: dict | None = None, precision: str = "bf16"):
         device = device or _default_device()
         self.vocoder = load_vocoder("vocos", is_local=bool(vocoder_path), local_path=vocoder_path, device=device, seed=seed,
-                                    state_dict=vocoder_state_dict)
+                                    state_dict=vocoder_state_dict, precision=precision)
         self.ema_model = load_model(None, model_cfg or dict(dim=1024, depth=22, heads=16, ff_mult=2, text_dim=512, conv_layers=4),
-                                    vocab_file=vocab_file, device=device, ckpt_path=ckpt_path, seed=seed, state_dict=state_dict)
+                                    vocab_file=vocab_file, device=device, ckpt_path=ckpt_path, seed=seed, state_dict=state_dict,
+                                    precision=precision)
         self.output_int16 = output_int16
         self.noise_fn = None          # tests: callable (chunk index, frames) -> [frames, 100] noise; None: fresh device draw
         self._prompts: dict[str, tuple] = {}

@@ -11,7 +11,7 @@ import sys
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libf5b200" + os.environ.get("F5_LIB_SUFFIX", "") + ".so")   # suffix: A/B builds of kernel variants
-SOURCES = ["gemm_tcgen05.cu", "attn_tcgen05.cu", "elementwise.cu", "vocos_istft.cu", "mel_frontend.cu"]
+SOURCES = ["gemm_tcgen05.cu", "attn_tcgen05.cu", "attn_f32.cu", "elementwise.cu", "vocos_istft.cu", "mel_frontend.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
               "-Xcompiler", "-fPIC", "-cudart", "static"]
 

@@ -12,7 +12,7 @@ __global__ void __launch_bounds__(256) layernorm_mod_kernel(const float* __restr
                                                             __nv_bfloat16* __restrict__ y, long long ldy,
                                                             float* __restrict__ y32, long long ldy32, int M,
                                                             const float* __restrict__ a, const float* __restrict__ b,
-                                                            float a_off, float eps) {
+                                                            float a_off, float eps, int lo_off) {
   pdl_wait();
   pdl_launch();
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -44,7 +44,17 @@ __global__ void __launch_bounds__(256) layernorm_mod_kernel(const float* __restr
     const float o1 = (v[i].y - mean) * rstd * (a_off + a4.y) + b4.y;
     const float o2 = (v[i].z - mean) * rstd * (a_off + a4.z) + b4.z;
     const float o3 = (v[i].w - mean) * rstd * (a_off + a4.w) + b4.w;
-    if (y != nullptr) yr[i * 32 + lane] = make_uint2(pack_bf16x2(o0, o1), pack_bf16x2(o2, o3));
+    if (y != nullptr) {
+      if (lo_off > 0) {                                        // split-operand mode: high plane here, low plane lo_off columns on
+        uint32_t h0, l0, h1, l1;
+        split_bf16x2(o0, o1, h0, l0);
+        split_bf16x2(o2, o3, h1, l1);
+        yr[i * 32 + lane] = make_uint2(h0, h1);
+        reinterpret_cast<uint2*>(y + static_cast<size_t>(row) * ldy + lo_off)[i * 32 + lane] = make_uint2(l0, l1);
+      } else {
+        yr[i * 32 + lane] = make_uint2(pack_bf16x2(o0, o1), pack_bf16x2(o2, o3));
+      }
+    }
     if (y32 != nullptr)
       reinterpret_cast<float4*>(y32 + static_cast<size_t>(row) * ldy32)[i * 32 + lane] = make_float4(o0, o1, o2, o3);
   }
@@ -61,7 +71,7 @@ __global__ void __launch_bounds__(256) dwconv7_ln_kernel(const float* __restrict
                                                          __nv_bfloat16* __restrict__ y, long long ldy, int M,
                                                          const int* __restrict__ row_pos, const float* __restrict__ w,
                                                          const float* __restrict__ bias, const float* __restrict__ ln_w,
-                                                         const float* __restrict__ ln_b, float eps) {
+                                                         const float* __restrict__ ln_b, float eps, int lo_off) {
   pdl_wait();
   pdl_launch();
   constexpr int C = NV * 128;
@@ -84,9 +94,13 @@ __global__ void __launch_bounds__(256) dwconv7_ln_kernel(const float* __restrict
       if (row >= M) break;
       uint2* yr = reinterpret_cast<uint2*>(y + static_cast<size_t>(row) * ldy);
       const int pos = row_pos[row];
+      uint2* yl = reinterpret_cast<uint2*>(y + static_cast<size_t>(row) * ldy + lo_off);   // low plane (split-operand mode)
       if (pos < 0) {
 #pragma unroll
-        for (int i = 0; i < NV; ++i) yr[i * 32 + lane] = make_uint2(0, 0);
+        for (int i = 0; i < NV; ++i) {
+          yr[i * 32 + lane] = make_uint2(0, 0);
+          if (lo_off > 0) yl[i * 32 + lane] = make_uint2(0, 0);
+        }
         continue;
       }
       float4 acc[NV];
@@ -123,9 +137,17 @@ __global__ void __launch_bounds__(256) dwconv7_ln_kernel(const float* __restrict
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
         const float4 a4 = lw[i * 32 + lane], b4 = lb[i * 32 + lane];
-        yr[i * 32 + lane] = make_uint2(
-            pack_bf16x2((acc[i].x - mean) * rstd * a4.x + b4.x, (acc[i].y - mean) * rstd * a4.y + b4.y),
-            pack_bf16x2((acc[i].z - mean) * rstd * a4.z + b4.z, (acc[i].w - mean) * rstd * a4.w + b4.w));
+        const float o0 = (acc[i].x - mean) * rstd * a4.x + b4.x, o1 = (acc[i].y - mean) * rstd * a4.y + b4.y;
+        const float o2 = (acc[i].z - mean) * rstd * a4.z + b4.z, o3 = (acc[i].w - mean) * rstd * a4.w + b4.w;
+        if (lo_off > 0) {
+          uint32_t h0, l0, h1, l1;
+          split_bf16x2(o0, o1, h0, l0);
+          split_bf16x2(o2, o3, h1, l1);
+          yr[i * 32 + lane] = make_uint2(h0, h1);
+          yl[i * 32 + lane] = make_uint2(l0, l1);
+        } else {
+          yr[i * 32 + lane] = make_uint2(pack_bf16x2(o0, o1), pack_bf16x2(o2, o3));
+        }
       }
     }
   }
@@ -198,6 +220,69 @@ __global__ void grn_apply_kernel(__nv_bfloat16* __restrict__ x, long long ldx, i
 }
 
 // ------------------------------------------------------------------------------------------------ gather / pack / misc
+// fp32 forms of the two GRN passes (fp32 precision mode: the pointwise GEMM's GELU output stays fp32 until it is split into
+// bf16 planes for the next GEMM); same fixed summation order as the bf16 kernels
+__global__ void __launch_bounds__(256) grn_sumsq_f32_kernel(const float* __restrict__ x, long long ldx, int C,
+                                                            const int* __restrict__ seg_rows, float* __restrict__ sumsq) {
+  pdl_wait();
+  pdl_launch();
+  __shared__ float2 part[4][64];
+  const int seg = blockIdx.y;
+  const int row0 = seg_rows[2 * seg], n = seg_rows[2 * seg + 1];
+  const int cp = threadIdx.x & 63, slice = threadIdx.x >> 6;
+  const int c2 = blockIdx.x * 64 + cp;
+  float s0 = 0.f, s1 = 0.f;
+  if (2 * c2 < C) {
+    for (int r = slice; r < n; r += 4) {
+      const float2 f = reinterpret_cast<const float2*>(x + static_cast<size_t>(row0 + r) * ldx)[c2];
+      s0 = fmaf(f.x, f.x, s0);
+      s1 = fmaf(f.y, f.y, s1);
+    }
+  }
+  part[slice][cp] = make_float2(s0, s1);
+  __syncthreads();
+  if (slice == 0 && 2 * c2 < C) {
+    const float2 a = part[0][cp], b = part[1][cp], c = part[2][cp], d = part[3][cp];
+    sumsq[static_cast<size_t>(seg) * C + 2 * c2] = (a.x + b.x) + (c.x + d.x);
+    sumsq[static_cast<size_t>(seg) * C + 2 * c2 + 1] = (a.y + b.y) + (c.y + d.y);
+  }
+}
+
+__global__ void grn_apply_f32_kernel(float* __restrict__ x, long long ldx, int C, const int* __restrict__ seg_rows,
+                                     const float* __restrict__ sumsq, const float* __restrict__ gamma,
+                                     const float* __restrict__ beta) {
+  pdl_wait();
+  pdl_launch();
+  __shared__ float red[32];
+  __shared__ float mean_gx;
+  const int seg = blockIdx.y;
+  const int row0 = seg_rows[2 * seg], n = seg_rows[2 * seg + 1];
+  const int r0 = blockIdx.x * GRN_ROWS;
+  if (r0 >= n) return;
+  const int r1 = min(n, r0 + GRN_ROWS);
+  float part = 0.f;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) part += sqrtf(sumsq[static_cast<size_t>(seg) * C + c]);
+  part = warp_sum(part);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = threadIdx.x < (blockDim.x + 31) / 32 ? red[threadIdx.x] : 0.f;
+    t = warp_sum(t);
+    if (threadIdx.x == 0) mean_gx = t / C;
+  }
+  __syncthreads();
+  const float inv = 1.f / (mean_gx + 1e-6f);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float nx = sqrtf(sumsq[static_cast<size_t>(seg) * C + c]) * inv;
+    const float g = gamma[c], b = beta[c];
+    for (int r = r0; r < r1; ++r) {
+      float* p = x + static_cast<size_t>(row0 + r) * ldx + c;
+      const float f = *p;
+      *p = g * (f * nx) + b + f;
+    }
+  }
+}
+
 __global__ void text_gather_pos_kernel(const int* __restrict__ ids, const int* __restrict__ row_pos,
                                        const float* __restrict__ emb, const float* __restrict__ pos_table, int max_pos,
                                        float* __restrict__ out, long long ldo, int M, int C) {
@@ -223,7 +308,7 @@ __global__ void text_gather_pos_kernel(const int* __restrict__ ids, const int* _
 __global__ void __launch_bounds__(256) pack_bf16_kernel(const float* __restrict__ src, long long lds,
                                                         __nv_bfloat16* __restrict__ dst, long long ldd, int dst_col,
                                                         int M, int C, int C_pad, const int* __restrict__ src_rows,
-                                                        const int* __restrict__ row_pos) {
+                                                        const int* __restrict__ row_pos, int lo_off) {
   pdl_wait();
   pdl_launch();
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -236,7 +321,14 @@ __global__ void __launch_bounds__(256) pack_bf16_kernel(const float* __restrict_
   for (int c = lane * 2; c < C_pad; c += 64) {
     const float v0 = (srow >= 0 && c < C) ? s[c] : 0.f;
     const float v1 = (srow >= 0 && c + 1 < C) ? s[c + 1] : 0.f;
-    *reinterpret_cast<uint32_t*>(d + c) = pack_bf16x2(v0, v1);
+    if (lo_off > 0) {
+      uint32_t h, l;
+      split_bf16x2(v0, v1, h, l);
+      *reinterpret_cast<uint32_t*>(d + c) = h;
+      *reinterpret_cast<uint32_t*>(d + lo_off + c) = l;
+    } else {
+      *reinterpret_cast<uint32_t*>(d + c) = pack_bf16x2(v0, v1);
+    }
   }
 }
 
@@ -336,16 +428,36 @@ __global__ void __launch_bounds__(256) randn_rows_kernel(float* __restrict__ x, 
 }
 
 __global__ void time_sinus_kernel(const float* __restrict__ t, int steps, const float* __restrict__ freqs, int dim,
-                                  __nv_bfloat16* __restrict__ out, long long ldo) {
+                                  __nv_bfloat16* __restrict__ out, long long ldo, int lo_off) {
   pdl_wait();
   pdl_launch();
   const int s = blockIdx.x;
   const int half = dim / 2;
   for (int k = threadIdx.x; k < half; k += blockDim.x) {
     const float arg = (1000.f * t[s]) * freqs[k];
-    out[static_cast<size_t>(s) * ldo + k] = __float2bfloat16(sinf(arg));
-    out[static_cast<size_t>(s) * ldo + half + k] = __float2bfloat16(cosf(arg));
+    const float sn = sinf(arg), cs = cosf(arg);
+    const __nv_bfloat16 hs = __float2bfloat16(sn), hc = __float2bfloat16(cs);
+    out[static_cast<size_t>(s) * ldo + k] = hs;
+    out[static_cast<size_t>(s) * ldo + half + k] = hc;
+    if (lo_off > 0) {
+      out[static_cast<size_t>(s) * ldo + lo_off + k] = __float2bfloat16(sn - __bfloat162float(hs));
+      out[static_cast<size_t>(s) * ldo + lo_off + half + k] = __float2bfloat16(cs - __bfloat162float(hc));
+    }
   }
+}
+
+// split-operand form: x [rows, cols] contiguous -> y [rows, 2 * cols]: high plane | low plane
+__global__ void silu_split_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, long long n, int cols) {
+  pdl_wait();
+  pdl_launch();
+  const long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 2;
+  if (i >= n) return;
+  const float2 v = *reinterpret_cast<const float2*>(x + i);
+  uint32_t h, l;
+  split_bf16x2(silu(v.x), silu(v.y), h, l);
+  const long long r = i / cols, c = i % cols;
+  *reinterpret_cast<uint32_t*>(y + r * 2 * cols + c) = h;
+  *reinterpret_cast<uint32_t*>(y + r * 2 * cols + cols + c) = l;
 }
 
 __global__ void silu_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, long long n) {
@@ -367,13 +479,14 @@ using namespace f5;
 #define F5_LAUNCH_RC() static_cast<int>(cudaGetLastError())
 
 extern "C" int f5_layernorm_mod(const float* x, int64_t ldx, void* y, int64_t ldy, float* y32, int64_t ldy32, int32_t M,
-                                int32_t D, const float* a, const float* b, float a_off, float eps, void* stream) {
-  if (!x || (!y && !y32) || !a || !b || M <= 0 || D % 128 != 0 || D > 1024 || ldx % 4 != 0 || ldy % 4 != 0 || ldy32 % 4 != 0)
+                                int32_t D, const float* a, const float* b, float a_off, float eps, int32_t lo_off, void* stream) {
+  if (!x || (!y && !y32) || !a || !b || M <= 0 || D % 128 != 0 || D > 1024 || ldx % 4 != 0 || ldy % 4 != 0 || ldy32 % 4 != 0 ||
+      lo_off < 0 || lo_off % 4 != 0)
     return F5_ERR_ARG;
   const int grid = (M + 7) / 8;
   __nv_bfloat16* yo = reinterpret_cast<__nv_bfloat16*>(y);
   switch (D / 128) {
-#define F5_CASE(NV) case NV: f5_launch(layernorm_mod_kernel<NV>, dim3(grid), dim3(256), 0, F5_STREAM(stream), x, ldx, yo, ldy, y32, ldy32, M, a, b, a_off, eps); break;
+#define F5_CASE(NV) case NV: f5_launch(layernorm_mod_kernel<NV>, dim3(grid), dim3(256), 0, F5_STREAM(stream), x, ldx, yo, ldy, y32, ldy32, M, a, b, a_off, eps, lo_off); break;
     F5_CASE(1) F5_CASE(2) F5_CASE(3) F5_CASE(4) F5_CASE(5) F5_CASE(6) F5_CASE(7) F5_CASE(8)
 #undef F5_CASE
   }
@@ -382,14 +495,15 @@ extern "C" int f5_layernorm_mod(const float* x, int64_t ldx, void* y, int64_t ld
 
 extern "C" int f5_dwconv7_ln(const float* x, int64_t ldx, void* y, int64_t ldy, int32_t M, int32_t C, const int32_t* row_pos,
                              const float* w, const float* bias, const float* ln_w, const float* ln_b, float eps,
-                             void* stream) {
-  if (!x || !y || !row_pos || !w || !bias || !ln_w || !ln_b || M <= 0 || C % 128 != 0 || C > 512 || ldx % 4 != 0 || ldy % 4 != 0)
+                             int32_t lo_off, void* stream) {
+  if (!x || !y || !row_pos || !w || !bias || !ln_w || !ln_b || M <= 0 || C % 128 != 0 || C > 512 || ldx % 4 != 0 || ldy % 4 != 0 ||
+      lo_off < 0 || lo_off % 4 != 0)
     return F5_ERR_ARG;
   const int blocks = (M + DW_ROWS_PER_CTA - 1) / DW_ROWS_PER_CTA;
   const int grid = blocks < kNumSMsB200 * 8 ? blocks : kNumSMsB200 * 8;
   __nv_bfloat16* yo = reinterpret_cast<__nv_bfloat16*>(y);
   switch (C / 128) {
-#define F5_CASE(NV) case NV: f5_launch(dwconv7_ln_kernel<NV>, dim3(grid), dim3(256), 0, F5_STREAM(stream), x, ldx, yo, ldy, M, row_pos, w, bias, ln_w, ln_b, eps); break;
+#define F5_CASE(NV) case NV: f5_launch(dwconv7_ln_kernel<NV>, dim3(grid), dim3(256), 0, F5_STREAM(stream), x, ldx, yo, ldy, M, row_pos, w, bias, ln_w, ln_b, eps, lo_off); break;
     F5_CASE(1) F5_CASE(2) F5_CASE(3) F5_CASE(4)
 #undef F5_CASE
   }
@@ -414,6 +528,22 @@ extern "C" int f5_grn_apply(void* x, int64_t ldx, int32_t C, const int32_t* seg_
   return F5_LAUNCH_RC();
 }
 
+extern "C" int f5_grn_sumsq_f32(const float* x, int64_t ldx, int32_t C, const int32_t* seg_rows, int32_t num_segs, float* sumsq,
+                                void* stream) {
+  if (!x || !seg_rows || !sumsq || num_segs <= 0 || C % 2 != 0 || ldx % 2 != 0) return F5_ERR_ARG;
+  dim3 grid((C + 127) / 128, num_segs);
+  f5_launch(grn_sumsq_f32_kernel, dim3(grid), dim3(256), 0, F5_STREAM(stream), x, ldx, C, seg_rows, sumsq);
+  return F5_LAUNCH_RC();
+}
+
+extern "C" int f5_grn_apply_f32(float* x, int64_t ldx, int32_t C, const int32_t* seg_rows, int32_t num_segs, const float* sumsq,
+                                const float* gamma, const float* beta, void* stream) {
+  if (!x || !seg_rows || !sumsq || !gamma || !beta || num_segs <= 0) return F5_ERR_ARG;
+  dim3 grid((max_seg_rows_hint + GRN_ROWS - 1) / GRN_ROWS, num_segs);
+  f5_launch(grn_apply_f32_kernel, dim3(grid), dim3(256), 0, F5_STREAM(stream), x, ldx, C, seg_rows, sumsq, gamma, beta);
+  return F5_LAUNCH_RC();
+}
+
 extern "C" int f5_text_gather_pos(const int32_t* ids, const int32_t* row_pos, const float* emb, const float* pos_table,
                                   int32_t max_pos, float* out, int64_t ldo, int32_t M, int32_t C, void* stream) {
   if (!ids || !row_pos || !emb || !pos_table || !out || M <= 0 || C % 4 != 0 || ldo % 4 != 0) return F5_ERR_ARG;
@@ -422,10 +552,11 @@ extern "C" int f5_text_gather_pos(const int32_t* ids, const int32_t* row_pos, co
 }
 
 extern "C" int f5_pack_bf16(const float* src, int64_t lds, void* dst, int64_t ldd, int32_t dst_col, int32_t M, int32_t C,
-                            int32_t C_pad, const int32_t* src_rows, const int32_t* row_pos, void* stream) {
-  if (!src || !dst || M <= 0 || C <= 0 || C_pad < C || C_pad % 2 != 0 || dst_col % 2 != 0 || ldd % 2 != 0) return F5_ERR_ARG;
+                            int32_t C_pad, const int32_t* src_rows, const int32_t* row_pos, int32_t lo_off, void* stream) {
+  if (!src || !dst || M <= 0 || C <= 0 || C_pad < C || C_pad % 2 != 0 || dst_col % 2 != 0 || ldd % 2 != 0 || lo_off < 0 || lo_off % 2 != 0)
+    return F5_ERR_ARG;
   f5_launch(pack_bf16_kernel, dim3((M + 7) / 8), dim3(256), 0, F5_STREAM(stream), src, lds, reinterpret_cast<__nv_bfloat16*>(dst), ldd, dst_col,
-                                                               M, C, C_pad, src_rows, row_pos);
+                                                               M, C, C_pad, src_rows, row_pos, lo_off);
   return F5_LAUNCH_RC();
 }
 
@@ -456,15 +587,21 @@ extern "C" int f5_randn_rows(float* x, int64_t ldx, int32_t M, int32_t C, const 
 }
 
 extern "C" int f5_time_sinus(const float* t, int32_t steps, const float* freqs, int32_t dim, void* out, int64_t ldo,
-                             void* stream) {
-  if (!t || !freqs || !out || steps <= 0 || dim <= 0 || dim % 2 != 0) return F5_ERR_ARG;
-  f5_launch(time_sinus_kernel, dim3(steps), dim3(128), 0, F5_STREAM(stream), t, steps, freqs, dim, reinterpret_cast<__nv_bfloat16*>(out), ldo);
+                             int32_t lo_off, void* stream) {
+  if (!t || !freqs || !out || steps <= 0 || dim <= 0 || dim % 2 != 0 || lo_off < 0) return F5_ERR_ARG;
+  f5_launch(time_sinus_kernel, dim3(steps), dim3(128), 0, F5_STREAM(stream), t, steps, freqs, dim, reinterpret_cast<__nv_bfloat16*>(out), ldo, lo_off);
   return F5_LAUNCH_RC();
 }
 
-extern "C" int f5_silu_bf16(const float* x, void* out, int64_t n, void* stream) {
-  if (!x || !out || n <= 0) return F5_ERR_ARG;
+extern "C" int f5_silu_bf16(const float* x, void* out, int64_t n, int32_t split_cols, void* stream) {
+  if (!x || !out || n <= 0 || split_cols < 0) return F5_ERR_ARG;
   const long long pairs = (n + 1) / 2;
+  if (split_cols > 0) {
+    if (split_cols % 2 != 0 || n % split_cols != 0) return F5_ERR_ARG;
+    f5_launch(silu_split_kernel, dim3(static_cast<unsigned>((pairs + 255) / 256)), dim3(256), 0, F5_STREAM(stream), x,
+              reinterpret_cast<__nv_bfloat16*>(out), n, split_cols);
+    return F5_LAUNCH_RC();
+  }
   f5_launch(silu_bf16_kernel, dim3(static_cast<unsigned>((pairs + 255) / 256)), dim3(256), 0, F5_STREAM(stream), 
       x, reinterpret_cast<__nv_bfloat16*>(out), n);
   return F5_LAUNCH_RC();

@@ -36,6 +36,7 @@ struct GemmCfg {
 struct GemmParams {
   int M, N, num_m_tiles, num_n_tiles, num_k;
   int kc_per_tap, tap_pad, a_grouped, b_tap_rows;
+  int taps_per_seg, a_lo_off;   // split-operand ("bf16x3") mode: see f5_gemm_args
   int mode, act;
   const float* bias;
   const float* gate;
@@ -140,14 +141,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       for (int tile = first_unit; tile < num_tiles; tile += num_walkers) {
         const int m0 = ((tile / p.num_n_tiles) * CL + cta_rank) * BLOCK_M;
         const int n0 = (tile % p.num_n_tiles) * BLOCK_N;
-        int tap = 0, kc = 0;
+        // tap = seg * taps_per_seg + t_in: t_in shifts the A rows (implicit conv), seg selects the operand planes of the
+        // split-operand mode (A_hi B_hi | A_hi B_lo | A_lo B_hi: B's planes are stacked by rows like taps, A's low plane sits
+        // a_lo_off columns to the right); dense / plain conv launches have one segment (taps_per_seg == num_taps)
+        int tap = 0, kc = 0, t_in = 0, a_plane = 0;
         for (int k = 0; k < p.num_k; ++k) {
           mbar_wait_warp(&empty_bar[stage], phase ^ 1, leader);
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + Cfg::A_BYTES;
           if (leader) {
             mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-            tma_load_2d(sa, &tmap_a, &full_bar[stage], (p.a_grouped ? n0 : 0) + kc * BLOCK_K, m0 + tap - p.tap_pad);
+            tma_load_2d(sa, &tmap_a, &full_bar[stage], (p.a_grouped ? n0 : 0) + kc * BLOCK_K + a_plane, m0 + t_in - p.tap_pad);
             if (CL == 1) {
               tma_load_2d(sb, &tmap_b, &full_bar[stage], kc * BLOCK_K, tap * p.b_tap_rows + n0);
             } else {   // my half of the B tile (BLOCK_N / 2 rows), into both CTAs; the other half arrives from the peer
@@ -156,7 +160,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             }
           }
           __syncwarp();
-          if (++kc == p.kc_per_tap) { kc = 0; ++tap; }
+          if (++kc == p.kc_per_tap) {
+            kc = 0;
+            ++tap;
+            if (++t_in == p.taps_per_seg) { t_in = 0; a_plane = (tap == 2 * p.taps_per_seg) ? p.a_lo_off : 0; }
+          }
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -600,6 +608,9 @@ extern "C" int f5_gemm_bf16(const f5_gemm_args* a, void* stream) {
   p.num_n_tiles = (a->N + a->block_n - 1) / a->block_n;
   p.num_k = a->num_taps * a->kc_per_tap;
   p.kc_per_tap = a->kc_per_tap; p.tap_pad = a->tap_pad; p.a_grouped = a->a_grouped; p.b_tap_rows = a->b_tap_rows;
+  p.taps_per_seg = a->taps_per_seg > 0 ? a->taps_per_seg : a->num_taps;
+  p.a_lo_off = a->a_lo_off;
+  if (a->taps_per_seg > 0 && (a->num_taps != 3 * a->taps_per_seg || a->a_lo_off <= 0 || (a->a_lo_off % 64) != 0)) return F5_ERR_ARG;
   p.mode = a->mode; p.act = a->act;
   p.bias = a->bias; p.gate = a->gate;
   p.out = a->out; p.ldo = a->ldo; p.out2 = a->out2; p.ldo2 = a->ldo2;

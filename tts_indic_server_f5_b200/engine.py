@@ -16,6 +16,7 @@ Every arithmetic op is a launcher of `libf5b200.so` (ops.py); torch provides dev
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass
 
 import torch
@@ -51,17 +52,26 @@ def _conv_pos_weight(w: torch.Tensor) -> torch.Tensor:
     return wt.reshape(K * D, 64).contiguous()
 
 
+def split_planes(w: torch.Tensor) -> torch.Tensor:
+    """fp32 weight [rows, K] -> the B operand of the split-operand GEMM mode: bf16 planes stacked by rows [hi | lo | hi] with
+    hi = bf16(w), lo = bf16(w - hi) (3 x rows; for a conv weight the rows are (tap, out) so each plane holds all taps)."""
+    w = w.float()
+    hi = w.to(BF16)
+    lo = (w - hi.float()).to(BF16)
+    return torch.cat([hi, lo, hi])
+
+
 class DiTWeights:
     """Device-resident weights in the layout the kernels consume (bf16 K-major GEMM operands, fp32 vectors)."""
 
-    def __init__(self, sd: dict, cfg: DiTConfig, device):
-        self.cfg = cfg
+    def __init__(self, sd: dict, cfg: DiTConfig, device, x3: bool = False):
+        self.cfg, self.x3 = cfg, x3
         p = "transformer."
         D, TD, mel, L = cfg.dim, cfg.text_dim, cfg.mel_dim, cfg.depth
         assert D % 256 == 0 and cfg.dim_head == 64 and cfg.heads * 64 == D and TD % 128 == 0 and mel <= MELP
 
         def bf(t):
-            return t.to(device=device, dtype=BF16).contiguous()
+            return split_planes(t).to(device).contiguous() if x3 else t.to(device=device, dtype=BF16).contiguous()
 
         def f32(t):
             return t.to(device=device, dtype=F32).contiguous()
@@ -136,31 +146,35 @@ class UtteranceInput:
 class Workspace:
     """Device buffers for one packed layout size; reused across batches of the same size."""
 
-    def __init__(self, cfg: DiTConfig, R: int, steps_pad: int, device):
+    def __init__(self, cfg: DiTConfig, R: int, steps_pad: int, device, x3: bool = False):
         D, TD, TI, FF, L = cfg.dim, cfg.text_dim, cfg.text_inner, cfg.ff_inner, cfg.depth
+        P = 2 if x3 else 1                     # fp32 mode: every bf16 GEMM operand is two planes, hi | lo, side by side
         z = lambda r, c, dt: torch.zeros(r, c, device=device, dtype=dt)  # noqa: E731
         self.R = R
         self.x = z(R, MELP, F32)               # ODE state
         self.x0 = z(R, MELP, F32)              # initial noise y0 (kept so a staged batch can be re-run)
         self.cond = z(R, MELP, F32)            # step_cond
-        self.xb = z(2 * R, MELP, BF16)         # bf16 copy of x for both CFG halves
+        self.xb = z(2 * R, P * MELP, BF16)     # bf16 copy of x for both CFG halves
         self.pred = z(2 * R, MELP, F32)
         self.xres = z(2 * R, D, F32)           # residual stream
         self.inv = z(2 * R, D, F32)            # W_c cond + W_t text + b
-        self.hb = z(2 * R, D, BF16)
-        self.ab = z(2 * R, D, BF16)            # conv-1 output / attention output
-        self.qkv = z(2 * R, 3 * D, BF16)
-        self.fb = z(2 * R, FF, BF16)
+        self.hb = z(2 * R, P * D, BF16)
+        self.ab = z(2 * R, P * D, BF16)        # conv-1 output / attention output
+        if x3:                                 # fp32 scratch for GEMM outputs that feed another GEMM (QKV, FF1, conv-1, pointwise-1)
+            self.s32 = z(2 * R, max(3 * D, FF, TI), F32)
+        else:
+            self.qkv = z(2 * R, 3 * D, BF16)
+        self.fb = z(2 * R, P * FF, BF16)
         self.te = z(2 * R, TD, F32)
-        self.tb = z(2 * R, TD, BF16)
-        self.gb = z(2 * R, TI, BF16)
-        self.act = z(2 * R, MELP + TD, BF16)
+        self.tb = z(2 * R, P * TD, BF16)
+        self.gb = z(2 * R, P * TI, BF16)
+        self.act = z(2 * R, P * (MELP + TD), BF16)
         self.ids = torch.zeros(2 * R, device=device, dtype=I32)
         self.row_pos = torch.full((2 * R,), -1, device=device, dtype=I32)
         self.cond_flag = torch.zeros(R, device=device, dtype=I32)
-        self.tsin = z(steps_pad, cfg.freq_embed_dim, BF16)
+        self.tsin = z(steps_pad, P * cfg.freq_embed_dim, BF16)
         self.th = z(steps_pad, D, F32)
-        self.thb = z(steps_pad, D, BF16)
+        self.thb = z(steps_pad, P * D, BF16)
         self.mod = z(steps_pad, (6 * L + 2) * D, F32)
         self.tgrid = torch.zeros(steps_pad + 1, device=device, dtype=F32)
         self.dts = torch.zeros(steps_pad, device=device, dtype=F32)
@@ -188,8 +202,14 @@ class Workspace:
 class F5Engine:
     """CUDA sampler for one set of DiT weights.  `sample_packed` is the device-resident hot path."""
 
-    def __init__(self, sd: dict, cfg: DiTConfig, device="cuda", use_graphs: bool = True):
+    def __init__(self, sd: dict, cfg: DiTConfig, device="cuda", use_graphs: bool = True, precision: str = "bf16"):
+        """precision: "bf16" (served path: bf16 tensor-core operands, fp32 everything else) or "fp32" (the reference as
+        deployed is fp32, core/managers.py:76): every GEMM runs in the split-operand mode — operands carried as hi + lo bf16
+        planes, three tcgen05 products per k-block — and attention runs in fp32 on the CUDA cores (attn_f32.cu)."""
         from ._lib import lib
+        if precision not in ("bf16", "fp32"):
+            raise ValueError("precision must be 'bf16' or 'fp32'")
+        self.precision, self.x3 = precision, precision == "fp32"
         if not torch.cuda.is_available():
             raise RuntimeError("F5Engine needs a CUDA device (sm_100a); there is no CPU fallback")
         dev = torch.device(device)
@@ -200,11 +220,13 @@ class F5Engine:
         if rc != 0:
             raise RuntimeError("libf5b200.so targets sm_100a (B200) only")
         self.cfg, self.device = cfg, dev
-        self.w = DiTWeights(sd, cfg, self.device)
+        self.w = DiTWeights(sd, cfg, self.device, self.x3)
         self.use_graphs = use_graphs
         self._ws: dict[tuple, Workspace] = {}        # LRU over (row count, slot) (insertion order = recency)
         self.max_workspaces = 4                       # ~30 KB of buffers per row: C2 (159 k rows) is 4.7 GB
         self.max_graphs_per_workspace = 8
+        self.pdl_max_rows = 16384                     # packed rows (incl. the CFG duplicate) up to which PDL is switched on
+        self.pdl_auto = os.environ.get("F5_PDL") is None   # an explicit F5_PDL=0/1 (A/B runs) or a test overrides the policy
         self.graph_captures = 0                       # statistics: captures vs replays of the step graph
         self.graph_replays = 0
 
@@ -216,7 +238,7 @@ class F5Engine:
         if ws is None:
             while len(self._ws) >= self.max_workspaces:            # evict the least recently used size (and its graphs)
                 self._ws.pop(next(iter(self._ws)))
-            ws = Workspace(self.cfg, R, 128, self.device)
+            ws = Workspace(self.cfg, R, 128, self.device, self.x3)
         self._ws[(R, slot)] = ws
         return ws
 
@@ -323,62 +345,96 @@ class F5Engine:
         ws.h2d_bytes = sum(v.numel() * v.element_size() for v in moved) + (0 if inject else 8 * len(utts))
         return ws
 
+    # ------------------------------------------------------------------------------------------ precision-aware building blocks
+    def _gemm_to_operand(self, ws: Workspace, A, W, out_b, N: int, *, act=ops.F5_ACT_NONE, bias=None, mask_rows=False, **kw) -> None:
+        """out_b = act(A W^T + bias) as the NEXT GEMM's operand.  bf16 mode: the tensor-core GEMM stores bf16 itself.  fp32 mode:
+        the split-operand GEMM stores fp32 into the scratch and `f5_pack_bf16` splits it into the hi | lo planes."""
+        if not self.x3:
+            ops.gemm(A, W, N=N, mode=ops.F5_EPI_STORE_BF16, act=act, bias=bias, out=out_b, row_pos=ws.row_pos if mask_rows else None,
+                     mask_rows=mask_rows, **kw)
+            return
+        s32 = ws.s32[:, :N]
+        ops.gemm(A, W, N=N, mode=ops.F5_EPI_STORE_F32, act=act, bias=bias, out=s32, split=True, **kw)
+        ops.pack_bf16(s32, out_b, 0, N, N, row_pos=ws.row_pos if mask_rows else None, lo_off=N)
+
+    def _lo(self, width: int) -> int:
+        return width if self.x3 else 0
+
     # ------------------------------------------------------------------------------------------ hoisted work
     def hoist(self, ws: Workspace, steps: int) -> None:
         """Step-invariant work: time/AdaLN vectors for all steps, text embedding (both CFG variants), W_c cond + W_t text + b."""
-        cfg, w, R = self.cfg, self.w, ws.R
-        D, TD = cfg.dim, cfg.text_dim
+        cfg, w, R, x3 = self.cfg, self.w, ws.R, self.x3
+        D, TD, TI = cfg.dim, cfg.text_dim, cfg.text_inner
         # --- time embedding + all modulation vectors (modules.py:648-658, :286, :307)
-        ops.time_sinus(ws.tgrid[:128], w.t_freqs, ws.tsin)
-        ops.gemm(ws.tsin, w.t0_w, mode=ops.F5_EPI_STORE_F32, bias=w.t0_b, out=ws.th)
-        ops.silu_bf16(ws.th, ws.thb)
-        ops.gemm(ws.thb, w.t2_w, mode=ops.F5_EPI_STORE_F32, bias=w.t2_b, out=ws.th)
-        ops.silu_bf16(ws.th, ws.thb)
-        ops.gemm(ws.thb, w.mod_w, mode=ops.F5_EPI_STORE_F32, bias=w.mod_b, out=ws.mod)
+        ops.time_sinus(ws.tgrid[:128], w.t_freqs, ws.tsin, lo_off=self._lo(cfg.freq_embed_dim))
+        ops.gemm(ws.tsin, w.t0_w, mode=ops.F5_EPI_STORE_F32, bias=w.t0_b, out=ws.th, split=x3)
+        ops.silu_bf16(ws.th, ws.thb, split=x3)
+        ops.gemm(ws.thb, w.t2_w, mode=ops.F5_EPI_STORE_F32, bias=w.t2_b, out=ws.th, split=x3)
+        ops.silu_bf16(ws.th, ws.thb, split=x3)
+        ops.gemm(ws.thb, w.mod_w, mode=ops.F5_EPI_STORE_F32, bias=w.mod_b, out=ws.mod, split=x3)
         # --- text embedding, conditional half = real tokens, unconditional half = all filler (dit.py:47-69)
         ops.text_gather_pos(ws.ids, ws.row_pos, w.emb, w.pos_table, ws.te)
         for blk in w.text_blocks:                                            # ConvNeXtV2Block, modules.py:259-269
-            ops.dwconv7_ln(ws.te, ws.tb, ws.row_pos, blk["dw_w"], blk["dw_b"], blk["ln_w"], blk["ln_b"])
-            ops.gemm(ws.tb, blk["pw1_w"], mode=ops.F5_EPI_STORE_BF16, act=ops.F5_ACT_GELU_ERF, bias=blk["pw1_b"], out=ws.gb)
-            ops.grn(ws.gb, ws.segs, ws.sumsq, blk["grn_g"], blk["grn_b"])
-            ops.gemm(ws.gb, blk["pw2_w"], mode=ops.F5_EPI_RESID_F32, bias=blk["pw2_b"], resid=ws.te)
+            ops.dwconv7_ln(ws.te, ws.tb, ws.row_pos, blk["dw_w"], blk["dw_b"], blk["ln_w"], blk["ln_b"], lo_off=self._lo(TD))
+            if not x3:
+                ops.gemm(ws.tb, blk["pw1_w"], mode=ops.F5_EPI_STORE_BF16, act=ops.F5_ACT_GELU_ERF, bias=blk["pw1_b"], out=ws.gb)
+                ops.grn(ws.gb, ws.segs, ws.sumsq, blk["grn_g"], blk["grn_b"])
+            else:                                                            # GELU and GRN in fp32, then split for pwconv2
+                s32 = ws.s32[:, :TI]
+                ops.gemm(ws.tb, blk["pw1_w"], mode=ops.F5_EPI_STORE_F32, act=ops.F5_ACT_GELU_ERF, bias=blk["pw1_b"], out=s32, split=True)
+                ops.grn_f32(s32, ws.segs, ws.sumsq, blk["grn_g"], blk["grn_b"], TI)
+                ops.pack_bf16(s32, ws.gb, 0, TI, TI, lo_off=TI)
+            ops.gemm(ws.gb, blk["pw2_w"], mode=ops.F5_EPI_RESID_F32, bias=blk["pw2_b"], resid=ws.te, split=x3)
         # --- A = [cond | text] (cond is zero in the unconditional half: drop_audio_cond, dit.py:82-83)
-        ops.pack_bf16(ws.cond, ws.act, 0, cfg.mel_dim, MELP, M=R)
-        ops.pack_bf16(ws.te, ws.act, MELP, TD, TD, row_pos=ws.row_pos)
-        ops.gemm(ws.act, w.wct, mode=ops.F5_EPI_STORE_F32, bias=w.proj_b, out=ws.inv)
+        ops.pack_bf16(ws.cond, ws.act, 0, cfg.mel_dim, MELP, M=R, lo_off=self._lo(MELP + TD))
+        ops.pack_bf16(ws.te, ws.act, MELP, TD, TD, row_pos=ws.row_pos, lo_off=self._lo(MELP + TD))
+        ops.gemm(ws.act, w.wct, mode=ops.F5_EPI_STORE_F32, bias=w.proj_b, out=ws.inv, split=x3)
         # --- bf16 copy of the initial state for both halves
-        ops.pack_bf16(ws.x, ws.xb, 0, cfg.mel_dim, MELP, row_pos=ws.row_pos, M=R)
-        ops.pack_bf16(ws.x, ws.xb[R:], 0, cfg.mel_dim, MELP, row_pos=ws.row_pos, M=R)
+        self._pack_state(ws)
+
+    def _pack_state(self, ws: Workspace) -> None:
+        R = ws.R
+        ops.pack_bf16(ws.x, ws.xb, 0, self.cfg.mel_dim, MELP, row_pos=ws.row_pos, M=R, lo_off=self._lo(MELP))
+        ops.pack_bf16(ws.x, ws.xb[R:], 0, self.cfg.mel_dim, MELP, row_pos=ws.row_pos, M=R, lo_off=self._lo(MELP))
 
     # ------------------------------------------------------------------------------------------ one Euler step
     def step(self, ws: Workspace, s: int, cfg_strength: float) -> None:
-        cfg, w, R = self.cfg, self.w, ws.R
-        D, L, H = cfg.dim, cfg.depth, cfg.heads
+        cfg, w, R, x3 = self.cfg, self.w, ws.R, self.x3
+        D, L, H, FF = cfg.dim, cfg.depth, cfg.heads, cfg.ff_inner
         mod = ws.mod[s]
+        conv = dict(M=2 * R, block_n=64, num_taps=w.conv_k, kc_per_tap=1, tap_pad=w.conv_k // 2, a_grouped=True, b_tap_rows=D)
         # input embedding: W_x x + (W_c cond + W_t text + b); conv position embedding + residual (dit.py:85-86)
-        ops.gemm(ws.xb, w.wx, mode=ops.F5_EPI_STORE_F32, out=ws.xres, addend=ws.inv, out2=ws.hb, row_pos=ws.row_pos,
-                 mask_rows=True)
-        ops.gemm(ws.hb, w.c1_w, M=2 * R, N=D, mode=ops.F5_EPI_STORE_BF16, act=ops.F5_ACT_MISH, bias=w.c1_b, out=ws.ab,
-                 row_pos=ws.row_pos, mask_rows=True, block_n=64, num_taps=w.conv_k, kc_per_tap=1, tap_pad=w.conv_k // 2,
-                 a_grouped=True, b_tap_rows=D)
-        ops.gemm(ws.ab, w.c2_w, M=2 * R, N=D, mode=ops.F5_EPI_RESID_F32, act=ops.F5_ACT_MISH, bias=w.c2_b, resid=ws.xres,
-                 block_n=64, num_taps=w.conv_k, kc_per_tap=1, tap_pad=w.conv_k // 2, a_grouped=True, b_tap_rows=D)
+        if not x3:
+            ops.gemm(ws.xb, w.wx, mode=ops.F5_EPI_STORE_F32, out=ws.xres, addend=ws.inv, out2=ws.hb, row_pos=ws.row_pos,
+                     mask_rows=True)
+        else:
+            ops.gemm(ws.xb, w.wx, mode=ops.F5_EPI_STORE_F32, out=ws.xres, addend=ws.inv, split=True)
+            ops.pack_bf16(ws.xres, ws.hb, 0, D, D, row_pos=ws.row_pos, lo_off=D)
+        self._gemm_to_operand(ws, ws.hb, w.c1_w, ws.ab, D, act=ops.F5_ACT_MISH, bias=w.c1_b, mask_rows=True, **conv)
+        ops.gemm(ws.ab, w.c2_w, N=D, mode=ops.F5_EPI_RESID_F32, act=ops.F5_ACT_MISH, bias=w.c2_b, resid=ws.xres, split=x3, **conv)
         for l, blk in enumerate(w.blocks):                                   # DiTBlock, modules.py:558-572
             m = mod[l * 6 * D:(l + 1) * 6 * D]
             shift_msa, scale_msa, gate_msa = m[0:D], m[D:2 * D], m[2 * D:3 * D]
             shift_mlp, scale_mlp, gate_mlp = m[3 * D:4 * D], m[4 * D:5 * D], m[5 * D:6 * D]
-            ops.layernorm_mod(ws.xres, ws.hb, scale_msa, shift_msa, 1.0)
-            ops.gemm(ws.hb, blk["qkv_w"], mode=ops.F5_EPI_STORE_BF16, bias=blk["qkv_b"], out=ws.qkv, row_pos=ws.row_pos,
-                     rope=w.rope, rope_period=D, rope_tiles=2)
-            ops.attention(ws.qkv, ws.tiles, ws.ab, H, 0, D, 2 * D, 0.125)
-            ops.gemm(ws.ab, blk["o_w"], mode=ops.F5_EPI_RESID_F32, bias=blk["o_b"], gate=gate_msa, resid=ws.xres)
-            ops.layernorm_mod(ws.xres, ws.hb, scale_mlp, shift_mlp, 1.0)
-            ops.gemm(ws.hb, blk["f1_w"], mode=ops.F5_EPI_STORE_BF16, act=ops.F5_ACT_GELU_TANH, bias=blk["f1_b"], out=ws.fb)
-            ops.gemm(ws.fb, blk["f2_w"], mode=ops.F5_EPI_RESID_F32, bias=blk["f2_b"], gate=gate_mlp, resid=ws.xres)
+            ops.layernorm_mod(ws.xres, ws.hb, scale_msa, shift_msa, 1.0, lo_off=self._lo(D))
+            if not x3:
+                ops.gemm(ws.hb, blk["qkv_w"], mode=ops.F5_EPI_STORE_BF16, bias=blk["qkv_b"], out=ws.qkv, row_pos=ws.row_pos,
+                         rope=w.rope, rope_period=D, rope_tiles=2)
+                ops.attention(ws.qkv, ws.tiles, ws.ab, H, 0, D, 2 * D, 0.125)
+            else:                                                            # fp32 Q / K / V, RoPE inside the fp32 attention kernel
+                qkv32 = ws.s32[:, :3 * D]
+                ops.gemm(ws.hb, blk["qkv_w"], mode=ops.F5_EPI_STORE_F32, bias=blk["qkv_b"], out=qkv32, split=True)
+                ops.attention_f32(qkv32, ws.tiles, ws.ab, H, 0, D, 2 * D, 0.125, rope=w.rope, lo_off=D)
+            ops.gemm(ws.ab, blk["o_w"], mode=ops.F5_EPI_RESID_F32, bias=blk["o_b"], gate=gate_msa, resid=ws.xres, split=x3)
+            ops.layernorm_mod(ws.xres, ws.hb, scale_mlp, shift_mlp, 1.0, lo_off=self._lo(D))
+            self._gemm_to_operand(ws, ws.hb, blk["f1_w"], ws.fb, FF, act=ops.F5_ACT_GELU_TANH, bias=blk["f1_b"])
+            ops.gemm(ws.fb, blk["f2_w"], mode=ops.F5_EPI_RESID_F32, bias=blk["f2_b"], gate=gate_mlp, resid=ws.xres, split=x3)
         mf = mod[6 * L * D:]
-        ops.layernorm_mod(ws.xres, ws.hb, mf[0:D], mf[D:2 * D], 1.0)          # AdaLayerNormZero_Final: (scale, shift)
-        ops.gemm(ws.hb, w.out_w, mode=ops.F5_EPI_STORE_F32, bias=w.out_b, out=ws.pred)
+        ops.layernorm_mod(ws.xres, ws.hb, mf[0:D], mf[D:2 * D], 1.0, lo_off=self._lo(D))          # AdaLayerNormZero_Final: (scale, shift)
+        ops.gemm(ws.hb, w.out_w, mode=ops.F5_EPI_STORE_F32, bias=w.out_b, out=ws.pred, split=x3)
         ops.cfg_euler(ws.x, ws.pred, R, cfg.mel_dim, ws.row_pos, ws.dts, s, cfg_strength, ws.xb, MELP)
+        if x3:
+            self._pack_state(ws)                                             # both planes of the next step's W_x operand
 
     def run_steps(self, ws: Workspace, steps: int, cfg_strength: float) -> None:
         # The graph bakes in addresses of this workspace's buffers and the launch parameters: row count (the workspace), padded
@@ -402,8 +458,7 @@ class F5Engine:
             ws.graph_launches[key] = _lib.launch_count - n0
             _lib.launch_count = n0
             ws.x.copy_(x_saved)                       # ... then restore the state the warm-up step advanced
-            ops.pack_bf16(ws.x, ws.xb, 0, self.cfg.mel_dim, MELP, row_pos=ws.row_pos, M=ws.R)
-            ops.pack_bf16(ws.x, ws.xb[ws.R:], 0, self.cfg.mel_dim, MELP, row_pos=ws.row_pos, M=ws.R)
+            self._pack_state(ws)
             while len(ws.graphs) >= self.max_graphs_per_workspace:
                 ws.graphs.pop(next(iter(ws.graphs)))
             self.graph_captures += 1
@@ -426,6 +481,11 @@ class F5Engine:
         """Device-resident hot path on a staged batch: hoisted work, the Euler loop, prompt re-insert (cfm.py:160-204)."""
         if cfg_strength < 1e-5:
             raise NotImplementedError("cfg_strength < 1e-5 (single-branch sampling, cfm.py:170-171) is not on the served path")
+        # Programmatic dependent launch pays where kernels are short (a single request: 5120 graph nodes of ~10 us, -3 % latency);
+        # on a full batch the same edges cost 4 % (measured same-box, profiles/README.md), so it is switched per batch size.
+        # The setting is baked into a step graph when it is captured, and graphs are keyed per workspace (= per size).
+        if self.pdl_auto:
+            _lib.lib.f5_set_pdl(1 if 2 * ws.R <= self.pdl_max_rows else 0)
         if generation is not None and generation != ws.generation:
             raise RuntimeError("this staged batch was overwritten: another batch of the same packed size was staged into its "
                                "workspace before it ran (stage -> run must not interleave with another stage of the same size)")

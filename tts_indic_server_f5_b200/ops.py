@@ -34,10 +34,20 @@ def pick_block_n(N: int, M: int | None = None) -> int:
 def gemm(A: torch.Tensor, B: torch.Tensor, *, M: int | None = None, N: int | None = None, mode: int, act: int = F5_ACT_NONE,
          bias=None, gate=None, out=None, out2=None, addend=None, resid=None, row_pos=None, mask_rows=False,
          rope=None, rope_period=0, rope_tiles=0, block_n: int | None = None,
-         num_taps=1, kc_per_tap: int | None = None, tap_pad=0, a_grouped=False, b_tap_rows=0, num_sms=0) -> None:
-    """D = A @ B^T with fused epilogue (see f5_gemm_bf16).  A [a_rows, K] bf16, B [b_rows, Kb] bf16."""
+         num_taps=1, kc_per_tap: int | None = None, tap_pad=0, a_grouped=False, b_tap_rows=0, num_sms=0,
+         split: bool = False) -> None:
+    """D = A @ B^T with fused epilogue (see f5_gemm_bf16).  A [a_rows, K] bf16, B [b_rows, Kb] bf16.
+    split: split-operand mode — A is [rows, 2K] = hi | lo planes, B holds the three row-stacked planes [hi | lo | hi] of each
+    tap (3 x the rows of the ordinary weight): D = A_hi B_hi^T + A_hi B_lo^T + A_lo B_hi^T."""
     assert A.dtype == BF16 and B.dtype == BF16 and A.is_cuda and B.is_cuda
     a = GemmArgs()
+    if split:
+        assert A.shape[1] % 128 == 0 and B.shape[0] % 3 == 0
+        a.taps_per_seg, a.a_lo_off = num_taps, A.shape[1] // 2
+        if num_taps == 1:
+            b_tap_rows = B.shape[0] // 3 if N is None else N
+            N = b_tap_rows
+        num_taps = 3 * num_taps
     a.A, a.B = ptr(A), ptr(B)
     a.lda, a.ldb = _ld(A), _ld(B)
     a.a_rows, a.a_cols = A.shape
@@ -46,7 +56,7 @@ def gemm(A: torch.Tensor, B: torch.Tensor, *, M: int | None = None, N: int | Non
     a.N = (B.shape[0] if num_taps == 1 else b_tap_rows) if N is None else N
     a.block_n = block_n or pick_block_n(a.N, a.M)
     a.num_taps = num_taps
-    a.kc_per_tap = kc_per_tap if kc_per_tap is not None else (B.shape[1] + 63) // 64
+    a.kc_per_tap = kc_per_tap if kc_per_tap is not None else (B.shape[1] + 63) // 64      # split: B has K columns, A has 2K
     a.tap_pad, a.a_grouped, a.b_tap_rows = tap_pad, int(a_grouped), b_tap_rows
     a.mode, a.act = mode, act
     for name, t, dt in (("bias", bias, F32), ("gate", gate, F32), ("row_pos", row_pos, I32), ("rope", rope, F32)):
@@ -71,6 +81,15 @@ def gemm(A: torch.Tensor, B: torch.Tensor, *, M: int | None = None, N: int | Non
     call("f5_gemm_bf16", C.byref(a), stream_ptr())
 
 
+def attention_f32(qkv: torch.Tensor, tiles: torch.Tensor, out: torch.Tensor, heads: int, q_col: int, k_col: int, v_col: int,
+                  softmax_scale: float = 0.125, rope: torch.Tensor | None = None, lo_off: int = 0) -> None:
+    """fp32 attention (fp32 precision mode): qkv fp32, out bf16 (lo_off > 0: hi | lo planes), RoPE on head 0 from `rope`."""
+    assert qkv.dtype == F32 and out.dtype == BF16 and tiles.dtype == I32 and tiles.is_contiguous() and tiles.shape[1] == 4
+    assert rope is None or (rope.dtype == F32 and rope.is_contiguous() and rope.shape[1] == 64)
+    call("f5_attention_f32", ptr(qkv), _ld(qkv), q_col, k_col, v_col, heads, ptr(tiles), tiles.shape[0], ptr(rope), ptr(out),
+         _ld(out), lo_off, float(softmax_scale), stream_ptr())
+
+
 def attention(qkv: torch.Tensor, tiles: torch.Tensor, out: torch.Tensor, heads: int, q_col: int, k_col: int, v_col: int,
               softmax_scale: float = 0.125) -> None:
     assert qkv.dtype == BF16 and out.dtype == BF16 and tiles.dtype == I32 and tiles.is_contiguous() and tiles.shape[1] == 4
@@ -79,18 +98,26 @@ def attention(qkv: torch.Tensor, tiles: torch.Tensor, out: torch.Tensor, heads: 
 
 
 def layernorm_mod(x: torch.Tensor, y: torch.Tensor | None, a: torch.Tensor, b: torch.Tensor, a_off: float, eps: float = 1e-6,
-                  M: int | None = None, y32: torch.Tensor | None = None) -> None:
+                  M: int | None = None, y32: torch.Tensor | None = None, lo_off: int = 0) -> None:
     assert x.dtype == F32 and a.dtype == F32 and b.dtype == F32
     assert (y is None or y.dtype == BF16) and (y32 is None or y32.dtype == F32)
     call("f5_layernorm_mod", ptr(x), _ld(x), ptr(y), _ld(y) if y is not None else 0, ptr(y32),
          _ld(y32) if y32 is not None else 0, x.shape[0] if M is None else M, x.shape[1], ptr(a), ptr(b),
-         float(a_off), float(eps), stream_ptr())
+         float(a_off), float(eps), lo_off, stream_ptr())
 
 
-def dwconv7_ln(x, y, row_pos, w, bias, ln_w, ln_b, eps: float = 1e-6) -> None:
+def dwconv7_ln(x, y, row_pos, w, bias, ln_w, ln_b, eps: float = 1e-6, lo_off: int = 0) -> None:
     assert x.dtype == F32 and y.dtype == BF16 and row_pos.dtype == I32 and w.dtype == F32 and w.is_contiguous()
     call("f5_dwconv7_ln", ptr(x), _ld(x), ptr(y), _ld(y), x.shape[0], x.shape[1], ptr(row_pos), ptr(w), ptr(bias),
-         ptr(ln_w), ptr(ln_b), float(eps), stream_ptr())
+         ptr(ln_w), ptr(ln_b), float(eps), lo_off, stream_ptr())
+
+
+def grn_f32(x: torch.Tensor, seg_rows: torch.Tensor, sumsq: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, C_: int) -> None:
+    """In-place GRN on fp32 activations (fp32 precision mode); x [rows, >= C_]."""
+    assert x.dtype == F32 and seg_rows.dtype == I32 and sumsq.dtype == F32
+    S = seg_rows.shape[0]
+    call("f5_grn_sumsq_f32", ptr(x), _ld(x), C_, ptr(seg_rows), S, ptr(sumsq), stream_ptr())
+    call("f5_grn_apply_f32", ptr(x), _ld(x), C_, ptr(seg_rows), S, ptr(sumsq), ptr(gamma), ptr(beta), stream_ptr())
 
 
 def grn(x: torch.Tensor, seg_rows: torch.Tensor, sumsq: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor) -> None:
@@ -107,10 +134,11 @@ def text_gather_pos(ids, row_pos, emb, pos_table, out) -> None:
          out.shape[0], out.shape[1], stream_ptr())
 
 
-def pack_bf16(src, dst, dst_col: int, C_: int, C_pad: int, src_rows=None, row_pos=None, M: int | None = None) -> None:
+def pack_bf16(src, dst, dst_col: int, C_: int, C_pad: int, src_rows=None, row_pos=None, M: int | None = None,
+              lo_off: int = 0) -> None:
     assert src.dtype == F32 and dst.dtype == BF16
     call("f5_pack_bf16", ptr(src), _ld(src), ptr(dst), _ld(dst), dst_col, dst.shape[0] if M is None else M, C_, C_pad,
-         ptr(src_rows), ptr(row_pos), stream_ptr())
+         ptr(src_rows), ptr(row_pos), lo_off, stream_ptr())
 
 
 def where_rows(x, c, flag, C_: int) -> None:
@@ -131,14 +159,16 @@ def randn_rows(x, C_: int, row_pos, row_utt, utt_seed, M: int | None = None) -> 
          stream_ptr())
 
 
-def time_sinus(t, freqs, out) -> None:
+def time_sinus(t, freqs, out, lo_off: int = 0) -> None:
     assert t.dtype == F32 and freqs.dtype == F32 and out.dtype == BF16
-    call("f5_time_sinus", ptr(t), t.shape[0], ptr(freqs), 2 * freqs.shape[0], ptr(out), _ld(out), stream_ptr())
+    call("f5_time_sinus", ptr(t), t.shape[0], ptr(freqs), 2 * freqs.shape[0], ptr(out), _ld(out), lo_off, stream_ptr())
 
 
-def silu_bf16(x, out) -> None:
+def silu_bf16(x, out, split: bool = False) -> None:
+    """out = silu(x); split: out is [rows, 2 * cols] = hi | lo planes of x [rows, cols]."""
     assert x.dtype == F32 and out.dtype == BF16 and x.is_contiguous() and out.is_contiguous()
-    call("f5_silu_bf16", ptr(x), ptr(out), x.numel(), stream_ptr())
+    assert not split or out.shape == (x.shape[0], 2 * x.shape[1])
+    call("f5_silu_bf16", ptr(x), ptr(out), x.numel(), x.shape[1] if split else 0, stream_ptr())
 
 
 def istft(spec, window, frames, seg, max_wav_len: int, wav, gains=None) -> None:

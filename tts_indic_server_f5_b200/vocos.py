@@ -19,8 +19,14 @@ VGAP = 8
 
 
 class VocosEngine:
-    def __init__(self, vsd: dict, vcfg: VocosConfig, device="cuda"):
+    def __init__(self, vsd: dict, vcfg: VocosConfig, device="cuda", precision: str = "bf16"):
+        """precision "fp32": split-operand GEMMs (hi + lo bf16 planes, three products per k-block), see engine.F5Engine."""
         from ._lib import lib
+        from .engine import split_planes
+        if precision not in ("bf16", "fp32"):
+            raise ValueError("precision must be 'bf16' or 'fp32'")
+        self.precision, self.x3 = precision, precision == "fp32"
+        x3 = self.x3
         if not torch.cuda.is_available() or lib.f5_device_check() != 0:
             raise RuntimeError("VocosEngine needs a B200 (sm_100a); there is no CPU fallback")
         device = torch.device(device)
@@ -29,7 +35,7 @@ class VocosEngine:
         self.cfg, self.device = vcfg, device
         C, I = vcfg.dim, vcfg.intermediate_dim
         assert vcfg.n_fft == 1024 and vcfg.hop == 256 and C % 128 == 0 and C <= 512 and vcfg.n_mels <= MELP
-        bf = lambda t: t.to(device=device, dtype=BF16).contiguous()      # noqa: E731
+        bf = lambda t: (split_planes(t).to(device).contiguous() if x3 else t.to(device=device, dtype=BF16).contiguous())  # noqa: E731
         f32 = lambda t: t.to(device=device, dtype=F32).contiguous()      # noqa: E731
         w = vsd["backbone.embed.weight"].float()                          # [C, n_mels, 7]
         wt = torch.zeros(7, C, MELP)
@@ -64,8 +70,11 @@ class VocosEngine:
         if b is None:
             C, I = self.cfg.dim, self.cfg.intermediate_dim
             z = lambda r, c, dt: torch.zeros(r, c, device=self.device, dtype=dt)  # noqa: E731
-            b = dict(melb=z(Rv, MELP, BF16), h=z(Rv, C, F32), v=z(Rv, C, F32), hb=z(Rv, C, BF16), ib=z(Rv, I, BF16),
+            P = 2 if self.x3 else 1                                          # fp32 mode: hi | lo planes side by side
+            b = dict(melb=z(Rv, P * MELP, BF16), h=z(Rv, C, F32), v=z(Rv, C, F32), hb=z(Rv, P * C, BF16), ib=z(Rv, P * I, BF16),
                      spec=z(Rv, self.spec_ld, F32), frames=z(Rv, self.cfg.n_fft, F32))
+            if self.x3:
+                b["s32"] = z(Rv, I, F32)
             while len(self._bufs) >= self.max_buffer_sets:
                 self._bufs.pop(next(iter(self._bufs)))
         self._bufs[Rv] = b                                                  # most recently used last
@@ -94,19 +103,24 @@ class VocosEngine:
         """src fp32 [*, >=n_mels] device mel rows; src_rows int32 [Rv] maps vocoder rows to src rows (-1 = zero row);
         seg int32 [S,4] = {row0, frames, wav_offset, 0} on the device.  Returns the flat fp32 waveform buffer
         (utterance i at its offset, 256*(frames[i]-1) samples).  Device-resident: no host copies."""
-        cfg, Rv = self.cfg, src_rows.shape[0]
+        cfg, Rv, x3 = self.cfg, src_rows.shape[0], self.x3
         b = self._buffers(Rv)
-        C = cfg.dim
-        ops.pack_bf16(src, b["melb"], 0, cfg.n_mels, MELP, src_rows=src_rows)
+        C, I = cfg.dim, cfg.intermediate_dim
+        lo = (lambda w: w) if x3 else (lambda w: 0)                          # low-plane offset of a w-wide operand
+        ops.pack_bf16(src, b["melb"], 0, cfg.n_mels, MELP, src_rows=src_rows, lo_off=lo(MELP))
         ops.gemm(b["melb"], self.emb_w, M=Rv, N=C, mode=ops.F5_EPI_STORE_F32, bias=self.emb_b, out=b["h"], num_taps=7,
-                 kc_per_tap=MELP // 64, tap_pad=3, b_tap_rows=C)
+                 kc_per_tap=MELP // 64, tap_pad=3, b_tap_rows=C, split=x3)
         ops.layernorm_mod(b["h"], None, self.norm_w, self.norm_b, 0.0, y32=b["v"])
         for blk in self.blocks:
-            ops.dwconv7_ln(b["v"], b["hb"], row_pos, blk["dw_w"], blk["dw_b"], blk["ln_w"], blk["ln_b"])
-            ops.gemm(b["hb"], blk["pw1_w"], mode=ops.F5_EPI_STORE_BF16, act=ops.F5_ACT_GELU_ERF, bias=blk["pw1_b"], out=b["ib"])
-            ops.gemm(b["ib"], blk["pw2_w"], mode=ops.F5_EPI_RESID_F32, bias=blk["pw2_b"], gate=blk["gamma"], resid=b["v"])
-        ops.layernorm_mod(b["v"], b["hb"], self.fin_w, self.fin_b, 0.0)
-        ops.gemm(b["hb"], self.head_w, mode=ops.F5_EPI_STORE_F32, bias=self.head_b, out=b["spec"], block_n=128)
+            ops.dwconv7_ln(b["v"], b["hb"], row_pos, blk["dw_w"], blk["dw_b"], blk["ln_w"], blk["ln_b"], lo_off=lo(C))
+            if not x3:
+                ops.gemm(b["hb"], blk["pw1_w"], mode=ops.F5_EPI_STORE_BF16, act=ops.F5_ACT_GELU_ERF, bias=blk["pw1_b"], out=b["ib"])
+            else:
+                ops.gemm(b["hb"], blk["pw1_w"], mode=ops.F5_EPI_STORE_F32, act=ops.F5_ACT_GELU_ERF, bias=blk["pw1_b"], out=b["s32"], split=True)
+                ops.pack_bf16(b["s32"], b["ib"], 0, I, I, lo_off=I)
+            ops.gemm(b["ib"], blk["pw2_w"], mode=ops.F5_EPI_RESID_F32, bias=blk["pw2_b"], gate=blk["gamma"], resid=b["v"], split=x3)
+        ops.layernorm_mod(b["v"], b["hb"], self.fin_w, self.fin_b, 0.0, lo_off=lo(C))
+        ops.gemm(b["hb"], self.head_w, mode=ops.F5_EPI_STORE_F32, bias=self.head_b, out=b["spec"], block_n=128, split=x3)
         wav = torch.empty(max(total, 1), device=self.device, dtype=F32)
         ops.istft(b["spec"], self.window, b["frames"], seg, 256 * max(max(frames) - 1, 1), wav, gains)
         return wav
