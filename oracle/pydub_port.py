@@ -227,3 +227,12 @@ def clip_reference(aseg, clip_short=True, show_info=print):
             aseg = aseg[:15000]
             show_info("Audio is over 15s, clipping short. (3)")
     return remove_silence_edges(aseg) + Seg.silent(duration=50)
+
+
+def remove_silence_for_generated_wav_seg(aseg):
+    """utils_infer.py:530-539 on a segment."""
+    non_silent_segs = split_on_silence(aseg, min_silence_len=1000, silence_thresh=-50, keep_silence=500, seek_step=10)
+    non_silent_wave = Seg.silent(duration=0)
+    for non_silent_seg in non_silent_segs:
+        non_silent_wave += non_silent_seg
+    return non_silent_wave

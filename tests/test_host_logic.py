@@ -325,3 +325,112 @@ def test_checkpoint_roundtrip_with_the_reference_modules_real_keys(tmp_path):
     torch.save({"model_state_dict": real}, str(tmp_path / "plain.pt"))
     sd = W.strip_checkpoint(torch.load(str(tmp_path / "plain.pt"), map_location="cpu", weights_only=True), use_ema=False)
     assert set(sd) >= {k for k in real if k.startswith("transformer.")}
+
+
+def test_continuous_scheduler_batches_concurrent_requests():
+    """Worker thread + bounded queue: requests submitted from several threads are drained together, every
+    future gets ITS request's result, back-pressure raises queue.Full, an engine error reaches every waiter of the batch."""
+    import queue
+    import threading
+    import time
+    from tts_indic_server_f5_b200.scheduler import ContinuousScheduler
+
+    class Prep:
+        def __init__(self, d):
+            self.duration = d
+
+    class FakeSyn:
+        def __init__(self):
+            self.calls, self.fail = [], False
+
+        def _prep(self, spec, speed, fixd):
+            return Prep(40 + len(spec.gen_text))
+
+        def generate(self, specs, nfe, cfg, sway, speed, fixd, return_mel=False):
+            time.sleep(0.05)                                     # the "GPU" is busy: later submissions pile up in the queue
+            if self.fail:
+                raise RuntimeError("CUDA error: unspecified launch failure")
+            self.calls.append(len(specs))
+            waves = [np.full(256 * 4, float(len(s.gen_text)), dtype=np.float32) for s in specs]
+            mels = [np.full((100, 5), float(len(s.gen_text)), dtype=np.float32) for s in specs]
+            return waves, mels
+
+    syn = FakeSyn()
+    cs = ContinuousScheduler(syn, max_queue=8, max_batch_requests=16, max_wait_ms=30.0, nfe_step=4)
+    audio = torch.zeros(1, 24000)
+    futs, lock = {}, threading.Lock()
+
+    def client(k):
+        f = cs.submit((audio, 24000), "ref. ", "x" * (k + 1), seed=k)
+        with lock:
+            futs[k] = f
+
+    ths = [threading.Thread(target=client, args=(k,)) for k in range(6)]
+    [t.start() for t in ths]
+    [t.join() for t in ths]
+    for k, f in futs.items():
+        wave, sr, mel = f.result(timeout=10)
+        assert sr == 24000 and float(wave[0]) == k + 1 and mel.shape == (100, 5)      # each future got its own request
+    assert sum(cs.batches) == 6 and max(cs.batches) >= 2                               # concurrent requests shared a batch
+    # back-pressure: a full queue refuses instead of growing
+    syn2 = FakeSyn()
+    cs2 = ContinuousScheduler(syn2, max_queue=1, max_batch_requests=1, max_wait_ms=0.0, nfe_step=4)
+    held = [cs2.submit((audio, 24000), "ref. ", "abc")]
+    with pytest.raises(queue.Full):
+        for _ in range(50):
+            held.append(cs2.submit((audio, 24000), "ref. ", "abc", timeout=0.0))
+    # an engine failure is delivered to the waiters
+    syn.fail = True
+    f = cs.submit((audio, 24000), "ref. ", "boom")
+    with pytest.raises(RuntimeError, match="launch failure"):
+        f.result(timeout=10)
+    cs.close()
+    cs2.close()
+    with pytest.raises(RuntimeError):
+        cs.submit((audio, 24000), "ref. ", "late")
+
+
+def test_out_of_line_wait_fits_the_low_register_warps():
+    """`mbar_wait_warp_slow` is the one device function the tcgen05 kernels CALL; its callers are the producer / MMA warps, which
+    run on 72 (attention) or 56 (GEMM with eight epilogue warps) registers after `setmaxnreg.dec`.  ptxas allocates the callee's
+    registers per kernel without knowing that budget, so the built library is checked: every register the callee touches must
+    exist in the calling warp."""
+    import shutil
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    from tts_indic_server_f5_b200 import _lib
+    sass = subprocess.run(["cuobjdump", "-sass", _lib.LIB], capture_output=True, text=True).stdout
+    body, cur = {}, None
+    for line in sass.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            cur = m.group(1)
+            body[cur] = []
+            continue
+        m = re.match(r"\s+/\*([0-9a-f]{4,})\*/\s+(.*?);", line)
+        if m and cur:
+            body[cur].append((int(m.group(1), 16), m.group(2)))
+    checked = 0
+    for fn, ins in body.items():
+        if "attn_d64_kernel" in fn:
+            budget = 72
+        elif "gemm_tcgen05_kernel" in fn and fn.split("gemm_tcgen05_kernelI")[1].startswith(("Li256ELi1ELi1ELi8", "Li256ELi2ELi1ELi8", "Li256ELi3ELi1ELi8",
+                                                                                             "Li256ELi1ELi2ELi8", "Li256ELi2ELi2ELi8", "Li256ELi3ELi2ELi8")):
+            budget = 56
+        else:
+            continue
+        targets = sorted({int(x, 16) for _, i in ins for x in re.findall(r"CALL\.REL\.NOINC (0x[0-9a-f]+)", i)})
+        for t in targets:
+            callee = []
+            for a, i in ins:
+                if a < t:
+                    continue
+                callee.append(i)
+                if "RET.REL" in i and not i.strip().startswith("@"):
+                    break
+            if not any("TRYWAIT" in i for i in callee):
+                continue
+            top = max(int(r) for i in callee for r in re.findall(r"\bR(\d+)\b", i))
+            assert top < budget, f"{fn}: out-of-line wait uses R{top}, the calling warp has {budget} registers"
+            checked += 1
+    assert checked >= 7

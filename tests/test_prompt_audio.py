@@ -121,3 +121,18 @@ def test_preprocess_ref_audio_text_writes_conditioned_wav(tmp_path):
     os.unlink(out_path)
     with pytest.raises(NotImplementedError):
         api.preprocess_ref_audio_text(str(src), "   ")
+
+
+def test_remove_silence_for_generated_wav(tmp_path):
+    """utils_infer.py:530-539 (`remove_sil`): in-place rewrite equals the pydub port on a wave with two long pauses."""
+    import shutil
+    rate = 24000
+    src = tmp_path / "gen.wav"
+    write_wav(src, synth(rate, [(0.3, "s"), (2.0, "v"), (1.8, "s"), (1.5, "v"), (2.4, "s"), (1.0, "v"), (0.2, "s")], 12), rate)
+    ref = P.remove_silence_for_generated_wav_seg(P.Seg.from_wav(str(src)))
+    work = tmp_path / "work.wav"
+    shutil.copy(src, work)
+    A.remove_silence_for_generated_wav(str(work))
+    with wave.open(str(work), "rb") as w:
+        got = w.readframes(w.getnframes())
+    assert got == ref._data and len(got) < os.path.getsize(src) - 2 * rate * 2       # well over a second of pause removed

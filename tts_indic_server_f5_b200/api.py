@@ -22,7 +22,8 @@ import torch
 from . import text as T
 from .engine import F5Engine, UtteranceInput
 from .melspec import PromptCache, mel_rows, mel_spectrogram
-from .scheduler import RequestScheduler, cross_fade  # noqa: F401
+from .prompt_audio import remove_silence_for_generated_wav  # noqa: F401
+from .scheduler import ContinuousScheduler, RequestScheduler, cross_fade  # noqa: F401
 from .synthetic import UtteranceSpec
 from .vocos import VocosEngine
 from .weights import (INDICF5, VOCOS_24K, DiTConfig, VocosConfig, infer_dit_config, make_dit_state_dict,

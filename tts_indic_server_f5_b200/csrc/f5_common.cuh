@@ -149,6 +149,32 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   mbar_wait_slow(smem_u32(bar), parity);
 }
+// Slow path of mbar_wait_warp, OUT OF LINE: it is reached only when the first poll fails, and inlining its poll loop + watchdog
+// at the ~45 wait sites of the attention kernel's MMA / producer loops inflates a loop whose instruction-cache footprint one
+// sub-partition shares with two softmax warps.  (Only the low-register producer / MMA warps call it: a call from the
+// setmaxnreg.inc regions does not register-allocate.)  No record from here, and twice the limit: a stuck pipeline stalls every
+// role of the CTA within microseconds, so the per-thread waits of the softmax / epilogue warps time out first and leave it.
+static __device__ __noinline__ void mbar_wait_warp_slow(uint32_t addr, uint32_t parity) {
+  long long t0 = 0;
+  for (uint32_t polls = 1;; ++polls) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t}\n"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (__all_sync(0xffffffffu, ok != 0)) return;
+    if ((polls & 4095u) == 0) {
+      long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t0 == 0) t0 = now;
+      if (now - t0 > 2 * F5_WATCHDOG_NS) __trap();
+    }
+  }
+}
+
 // Wait of a whole producer / MMA warp that walks its loop warp-uniformly with ONE elected lane issuing (TMA, tcgen05.mma,
 // commits).  All 32 lanes poll together and the warp leaves only when EVERY lane has seen the phase complete in the same
 // poll (one VOTE.ALL on top of the try_wait; the loop condition is warp-uniform, so there is no divergence and the issue
@@ -170,28 +196,16 @@ __device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, b
   __syncwarp();
 #else
   const uint32_t addr = smem_u32(bar);
-  long long t0 = 0;
-  for (uint32_t polls = 1;; ++polls) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred P;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, P;\n\t}\n"
-        : "=r"(ok)
-        : "r"(addr), "r"(parity)
-        : "memory");
-    if (__all_sync(0xffffffffu, ok != 0)) return;
-    if ((polls & 4095u) == 0) {
-      long long now;
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-      if (t0 == 0) t0 = now;
-      // No record from here, and twice the limit: these waits are inlined ~45 times into the attention kernel's MMA / producer
-      // loops, and the record's instructions at every site cost 5 % of that kernel (instruction-cache footprint of a loop one
-      // sub-partition shares with two softmax warps).  A stuck pipeline stalls every role of the CTA within microseconds, so
-      // the per-thread waits of the softmax / epilogue warps (mbar_wait, mbar_wait_a) time out first and leave the record.
-      if (now - t0 > 2 * F5_WATCHDOG_NS) __trap();
-    }
-  }
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}\n"
+      : "=r"(ok)
+      : "r"(addr), "r"(parity)
+      : "memory");
+  if (__all_sync(0xffffffffu, ok != 0)) return;
+  mbar_wait_warp_slow(addr, parity);
 #endif
 }
 // Variants on a 32-bit shared-window address computed ONCE by the caller (the generic-pointer forms re-derive the window

@@ -145,6 +145,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         // split-operand mode (A_hi B_hi | A_hi B_lo | A_lo B_hi: B's planes are stacked by rows like taps, A's low plane sits
         // a_lo_off columns to the right); dense / plain conv launches have one segment (taps_per_seg == num_taps)
         int tap = 0, kc = 0, t_in = 0, a_plane = 0;
+#pragma unroll 1
         for (int k = 0; k < p.num_k; ++k) {
           mbar_wait_warp(&empty_bar[stage], phase ^ 1, leader);
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
@@ -195,6 +196,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         mbar_wait_warp(&tmem_empty[acc], acc_phase ^ 1, leader);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+#pragma unroll 1
         for (int k = 0; k < p.num_k; ++k) {
           mbar_wait_warp(&full_bar[stage], phase, leader);
           tc_fence_after();

@@ -5,6 +5,7 @@ is no fallback: if the CUDA library cannot run the op, the call raises.
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import torch
 
@@ -20,11 +21,18 @@ def _ld(t: torch.Tensor) -> int:
     return t.stride(0)
 
 
+SMALL_M_TILES = int(os.environ.get("F5_SMALL_M_TILES", "74"))   # 0 switches the small-batch rule off (A/B runs)
+
+
 def pick_block_n(N: int, M: int | None = None) -> int:
-    """Tile width of the persistent GEMM: 256 wherever N allows (one A tile feeds 256 columns).  An M-aware choice (narrower
-    tiles when 256-wide ones leave SMs idle on small batches) was measured at a single utterance and bought 1 ms of 65:
-    not worth a second kernel configuration on the hot path."""
+    """Tile width of the persistent GEMM: 256 wherever N allows (one A tile feeds 256 columns), EXCEPT when that leaves more
+    than half of the 148 SMs without a tile (a single request: M = 1792 rows, N = 1024 -> 56 tiles).  There the kernel is bound
+    by what ONE SM can pull from L2 (each of the few CTAs streams a whole 256-row weight slab: ~1.5 MB at ~120 GB/s = 12 us
+    for a 4 us MMA chain, ncu launch list profiles/r02_launches_c1.csv), and 128-wide tiles put twice as many SMs on the same
+    bytes."""
     if N % 256 == 0:
+        if M is not None and SMALL_M_TILES > 0 and N % 128 == 0 and ((M + 127) // 128) * (N // 256) <= SMALL_M_TILES:
+            return 128
         return 256
     if N >= 128:
         return 128

@@ -291,3 +291,18 @@ def preprocess_ref_audio(ref_audio_orig: str, clip_short=True, show_info=print) 
         name = f.name
     seg.export_wav(name)
     return name
+
+
+def remove_silence_segment(seg: PcmSegment) -> PcmSegment:
+    """utils_infer.py:530-539 on a segment: keep the non-silent stretches (>= 1 s below -50 dBFS counts as silence, 500 ms of it
+    kept on each side) and join them."""
+    out = seg.spawn(seg.data[:0])
+    for s in split_on_silence(seg, min_silence_len=1000, silence_thresh=-50, keep_silence=500, seek_step=10):
+        out = out + s
+    return out
+
+
+def remove_silence_for_generated_wav(filename: str) -> None:
+    """`remove_silence_for_generated_wav(filename)` (utils_infer.py:530-539; the `remove_sil` option of the CLI / gradio paths, off on
+    the served path): rewrites the WAV file in place."""
+    remove_silence_segment(PcmSegment.from_file(filename)).export_wav(filename)

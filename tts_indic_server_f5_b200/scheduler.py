@@ -139,3 +139,74 @@ class RequestScheduler:
             out[r.rid] = (cross_fade([waves[k] for k in idx], r.cross_fade_duration), TARGET_SR,
                           np.concatenate([mels[k] for k in idx], axis=1))
         return out
+
+
+class ContinuousScheduler:
+    """The serving loop the reference lacks (its route runs the model on the event-loop thread, one request at a time:
+    src/server/routes/speech.py:19-41).  Requests arrive from any thread through `submit()` (a bounded queue: back-pressure
+    instead of unbounded memory), ONE worker thread owns the GPU: it drains whatever is waiting — after the first request it
+    lingers `max_wait_ms` for company, up to `max_batch_requests` — and runs the drained set through `RequestScheduler` (chunks
+    of all requests length-bucketed into packed batches, per-request cross-fade).  Callers get a `concurrent.futures.Future`
+    resolving to the reference's `infer_process` triple (wave fp32, 24000, mel [100, F]).  An `async` route awaits
+    `asyncio.wrap_future(scheduler.submit(...))` and the event loop stays free."""
+
+    def __init__(self, synthesizer, max_queue: int = 256, max_batch_requests: int = 64, max_wait_ms: float = 4.0, **sched_kw):
+        import queue
+        import threading
+        self._sched = RequestScheduler(synthesizer, **sched_kw)
+        self._q: "queue.Queue" = queue.Queue(maxsize=max_queue)
+        self.max_batch_requests, self.max_wait_ms = max_batch_requests, max_wait_ms
+        self.batches: list[int] = []                 # requests per executed batch (observability / tests)
+        self._stop = threading.Event()
+        self._worker = threading.Thread(target=self._loop, name="f5-scheduler", daemon=True)
+        self._worker.start()
+
+    def submit(self, ref_audio, ref_text: str, gen_text: str, *, timeout: float | None = None, **kw):
+        """Queue a request; raises `queue.Full` after `timeout` seconds if the queue stays full (HTTP 503 material)."""
+        from concurrent.futures import Future
+        if self._stop.is_set():
+            raise RuntimeError("scheduler is closed")
+        fut: Future = Future()
+        self._q.put((fut, ref_audio, ref_text, gen_text, kw), timeout=timeout)
+        return fut
+
+    def _loop(self) -> None:
+        import queue
+        import time
+        while not self._stop.is_set():
+            try:
+                first = self._q.get(timeout=0.05)
+            except queue.Empty:
+                continue
+            items = [first]
+            deadline = time.monotonic() + self.max_wait_ms * 1e-3
+            while len(items) < self.max_batch_requests:
+                left = deadline - time.monotonic()
+                try:
+                    items.append(self._q.get(timeout=left) if left > 0 else self._q.get_nowait())
+                except queue.Empty:
+                    break
+            rids = []
+            try:
+                for fut, ref_audio, ref_text, gen_text, kw in items:
+                    rids.append(self._sched.submit(ref_audio, ref_text, gen_text, **kw))
+                out = self._sched.run()
+                self.batches.append(len(items))
+                for (fut, *_), rid in zip(items, rids):
+                    fut.set_result(out[rid])
+            except BaseException as e:  # noqa: BLE001 — every waiter must hear about it (a CUDA error is sticky)
+                self._sched.pending = []
+                for fut, *_ in items:
+                    if not fut.done():
+                        fut.set_exception(e)
+
+    def close(self, timeout: float = 5.0) -> None:
+        self._stop.set()
+        self._worker.join(timeout)
+        import queue
+        while True:                                   # nobody is left waiting on a dead worker
+            try:
+                fut, *_ = self._q.get_nowait()
+            except queue.Empty:
+                break
+            fut.set_exception(RuntimeError("scheduler closed"))
