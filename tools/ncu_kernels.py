@@ -27,11 +27,14 @@ xres = torch.randn(M, D, device=dev)
 gate = torch.randn(D, device=dev)
 tiles = L.attn_tiles.to(dev)
 W2 = (torch.randn(D, 2 * D, device=dev) / 45).to(torch.bfloat16)
-for rep in range(1):           # launch order per repetition: QKV, attention, out-proj, FF1, FF2 (one DiT layer)
+scale, shift = torch.randn(D, device=dev) * 0.1, torch.randn(D, device=dev) * 0.1
+hb = torch.zeros(M, D, device=dev, dtype=torch.bfloat16)
+for rep in range(1):           # launch order per repetition: QKV, attention, out-proj, FF1, FF2, LayerNorm (one DiT layer)
     ops.gemm(A, Wqkv, mode=ops.F5_EPI_STORE_BF16, bias=bias3, out=qkv)
     ops.attention(qkv, tiles, ab, 16, 0, D, 2 * D, 0.125)
     ops.gemm(ab, Wo, mode=ops.F5_EPI_RESID_F32, bias=bias1, gate=gate, resid=xres)
     ops.gemm(A, W1, mode=ops.F5_EPI_STORE_BF16, act=ops.F5_ACT_GELU_TANH, bias=bias2, out=fb)
     ops.gemm(fb, W2, mode=ops.F5_EPI_RESID_F32, bias=bias1, gate=gate, resid=xres)
+    ops.layernorm_mod(xres, hb, scale, shift, 1.0)
 torch.cuda.synchronize()
 print("ok rows", M, "tiles", tiles.shape[0])

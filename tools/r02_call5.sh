@@ -5,7 +5,7 @@ O=gpurun_out/c5
 timeout 900 python -m pytest tests -m gpu -x -q > $O/pytest.log 2>&1; echo "pytest rc=$?" | tee -a $O/summary.txt
 timeout 200 python tools/attn_bench.py > $O/attn_bench.txt 2>&1
 timeout 200 python tools/gemm_bench.py > $O/gemm_bench.txt 2>&1
-F5_SMALL_M_TILES=0 timeout 300 python tools/latency_c1.py >> $O/latency.txt 2>&1
+F5_SMALL_M_RULE=0 timeout 300 python tools/latency_c1.py >> $O/latency.txt 2>&1
 timeout 300 python tools/latency_c1.py >> $O/latency.txt 2>&1
 F5_PDL=0 timeout 300 python tools/latency_c1.py >> $O/latency.txt 2>&1
 timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > $O/bench.json 2> $O/bench.err; echo "bench rc=$?" | tee -a $O/summary.txt

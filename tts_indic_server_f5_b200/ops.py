@@ -21,18 +21,24 @@ def _ld(t: torch.Tensor) -> int:
     return t.stride(0)
 
 
-SMALL_M_TILES = int(os.environ.get("F5_SMALL_M_TILES", "74"))   # 0 switches the small-batch rule off (A/B runs)
+SMALL_M_RULE = os.environ.get("F5_SMALL_M_RULE", "1") != "0"   # 0 switches the small-batch rule off (A/B runs)
+NUM_SMS = 148
+COST_128 = 0.58    # time of a 128-wide tile relative to a 256-wide one of the same K (same A tile, half the B tile and MMA work)
 
 
 def pick_block_n(N: int, M: int | None = None) -> int:
-    """Tile width of the persistent GEMM: 256 wherever N allows (one A tile feeds 256 columns), EXCEPT when that leaves more
-    than half of the 148 SMs without a tile (a single request: M = 1792 rows, N = 1024 -> 56 tiles).  There the kernel is bound
-    by what ONE SM can pull from L2 (each of the few CTAs streams a whole 256-row weight slab: ~1.5 MB at ~120 GB/s = 12 us
-    for a 4 us MMA chain, ncu launch list profiles/r02_launches_c1.csv), and 128-wide tiles put twice as many SMs on the same
-    bytes."""
+    """Tile width of the persistent GEMM.  256 wherever N allows (one A tile feeds 256 columns) EXCEPT where the tile count is
+    so small that whole waves of SMs stand idle — a single request has M = 1792 rows: 56 tiles for the N = 1024 GEMMs (92 SMs
+    idle, and each busy one streams a 1.5 MB weight slab through its own ~120 GB/s L2 port: 12 us for a 4 us MMA chain, ncu
+    launch list profiles/r02_launches_c1.csv), 168 tiles = two waves of 148 for QKV.  The rule compares waves x tile cost of
+    the two widths; for a full batch (thousands of tiles) it always answers 256."""
     if N % 256 == 0:
-        if M is not None and SMALL_M_TILES > 0 and N % 128 == 0 and ((M + 127) // 128) * (N // 256) <= SMALL_M_TILES:
-            return 128
+        if M is not None and SMALL_M_RULE and N % 128 == 0:
+            mt = (M + 127) // 128
+            waves_256 = -(-(mt * (N // 256)) // NUM_SMS)
+            waves_128 = -(-(mt * (N // 128)) // NUM_SMS)
+            if waves_128 * COST_128 < waves_256:
+                return 128
         return 256
     if N >= 128:
         return 128
