@@ -14,6 +14,7 @@ from __future__ import annotations
 
 import logging
 import os
+import threading
 from dataclasses import dataclass
 
 import numpy as np
@@ -215,6 +216,8 @@ def load_model(model_cls=None, model_cfg=None, mel_spec_type=mel_spec_type, voca
             state_dict = strip_checkpoint(torch.load(ckpt_path, map_location="cpu", weights_only=True), use_ema)
     if state_dict is not None:
         cfg = infer_dit_config(state_dict)
+        if vocab_size > cfg.vocab_size:      # nn.Embedding would raise IndexError on the first out-of-range token (dit.py:56)
+            raise ValueError(f"the vocabulary has {vocab_size} entries but the checkpoint's text embedding holds {cfg.vocab_size}")
     else:
         kw = dict(model_cfg or {})
         base = INDICF5
@@ -298,6 +301,7 @@ class Synthesizer:
         self.last_d2h_bytes = 0
         self.prompt_cache = PromptCache()
         self._host_wav: torch.Tensor | None = None
+        self._lock = threading.RLock()     # stage -> run -> D2H of one call share workspaces and the landing buffer
 
     def _prep(self, spec: UtteranceSpec, speed_, fix_duration_) -> _Prepared:
         audio = spec.audio
@@ -396,7 +400,12 @@ class Synthesizer:
     def generate(self, specs: list[UtteranceSpec], nfe_step=nfe_step, cfg_strength=cfg_strength,
                  sway_sampling_coef=sway_sampling_coef, speed=speed, fix_duration=fix_duration, y0: list | None = None,
                  return_mel: bool = False, noise_seed: int | None = None):
-        """-> list of np.float32 waves (and optionally list of np mel [100, F_gen]); host in, host out."""
+        """-> list of np.float32 waves (and optionally list of np mel [100, F_gen]); host in, host out.  Calls from several
+        threads are serialised (the engine's workspaces and the pinned landing buffer belong to one batch at a time)."""
+        with self._lock:
+            return self._generate_locked(specs, nfe_step, cfg_strength, sway_sampling_coef, speed, fix_duration, y0, return_mel, noise_seed)
+
+    def _generate_locked(self, specs, nfe_step, cfg_strength, sway_sampling_coef, speed, fix_duration, y0, return_mel, noise_seed):
         wav, offs, frames, tot, ws, layout, preps = self.generate_device(specs, nfe_step, cfg_strength, sway_sampling_coef,
                                                                          speed, fix_duration, y0, noise_seed)
         if self._host_wav is None or self._host_wav.numel() < tot:                # persistent pinned landing buffer (grown, never

@@ -91,14 +91,17 @@ class PromptCache:
 
     @staticmethod
     def key(audio: torch.Tensor) -> tuple:
-        """Content key of a prompt: length + three 64-bit integer checksums of the sample bit patterns (all samples, and two
-        coprime-strided subsets) + the first and last 8 samples.  ~30 us per 5 s prompt (a cryptographic hash of the 480 KB
-        costs more than the mel kernel it saves)."""
+        """Content key of a prompt: length + CRC-32 of all sample bytes + two 64-bit integer checksums of coprime-strided subsets
+        of the sample bit patterns + the first and last 8 samples: ~0.25 ms per 5 s prompt.  Not an adversarial hash (a
+        cryptographic one over the 480 KB costs more than the mel kernel it saves); for an accidental collision a different
+        waveform of the same length would have to match the CRC and 128 bits of sums at once."""
+        import zlib
         a = audio.detach().reshape(-1)
         if a.device.type != "cpu" or a.dtype != torch.float32:
             a = a.float().cpu()
-        w = a.contiguous().view(torch.int32)
-        return (int(w.numel()), int(w.sum(dtype=torch.int64)), int(w[::7].sum(dtype=torch.int64)), int(w[3::11].sum(dtype=torch.int64)),
+        a = a.contiguous()
+        w = a.view(torch.int32)
+        return (int(w.numel()), zlib.crc32(a.numpy().data), int(w[::7].sum(dtype=torch.int64)), int(w[3::11].sum(dtype=torch.int64)),
                 a[:8].numpy().tobytes(), a[-8:].numpy().tobytes())
 
     def get(self, k, device):
