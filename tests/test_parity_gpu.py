@@ -497,3 +497,35 @@ def test_fp32_mode_full_size_c1_vs_reference_golden(golden_dir):
     assert r < FP32_MEL_REL and li < FP32_MEL_LINF and s > FP32_WAVE_SNR
     del model, voc
     torch.cuda.empty_cache()
+
+
+def test_trajectory_and_fp32_forward_at_c2_length(tiny_models, golden_dir):
+    """(1) `return_trajectory=True` reproduces torchdiffeq's stacked states (cfm.py:200: steps + 1 of them, the first is y0, the
+    last is the state BEFORE the prompt re-insert) against the oracle's odeint; (2) the fp32 mode at a benchmark length: full
+    IndicF5 forward pair at n = 1384 against the real reference, its own tolerance."""
+    cfg, _, sd, _, model, _ = tiny_models
+    vocab = {t: i for i, t in enumerate(T.synthetic_indic_vocab())}
+    mel = O.mel_spectrogram(S.prompt_audio(0.5, 1)).permute(0, 2, 1)
+    texts = [T.convert_char_to_pinyin([T.synthetic_indic_text(30, 4)])[0]]
+    y0 = [S.initial_noise(100, 0)]
+    out, traj = model.sample(cond=mel, text=texts, duration=90, steps=6, cfg_strength=2.0, sway_sampling_coef=-1.0, y0=y0,
+                             return_trajectory=True)
+    with torch.inference_mode():
+        ref_out, ref_traj = O.cfm_sample(sd, cfg, mel, O.list_str_to_idx(texts, vocab), 90, y0=y0[0], steps=6, return_trajectory=True)
+    assert traj.shape == (7, 1, 90, 100) and tuple(ref_traj.shape) == (7, 1, 90, 100)
+    assert torch.equal(traj[0, 0].cpu(), y0[0][:90])                            # state 0 is the injected noise, untouched
+    for k in range(1, 7):
+        assert rel(traj[k].cpu().numpy(), ref_traj[k].numpy()) < MEL_REL, k
+    assert rel(out.cpu().numpy(), ref_out.numpy()) < MEL_REL
+    plain, last = model.sample(cond=mel, text=texts, duration=90, steps=6, cfg_strength=2.0, sway_sampling_coef=-1.0, y0=y0)
+    assert torch.equal(plain, out) and last.shape == (1, 1, 90, 100)            # graph replay == the eager trajectory run
+    m32 = api.load_model(state_dict=W.make_dit_state_dict(W.INDICF5, seed=0), precision="fp32")
+    g = np.load(os.path.join(golden_dir, "full_fwd.npz"))
+    x, cond, text = S.forward_inputs(1384, W.INDICF5.vocab_size)
+    u = UtteranceInput(cond=cond[0], text_ids=text[0], n=1384, cond_len=1384, y0=x[0])
+    pc = m32.engine.forward_flow([u], 0.37)[0].cpu().numpy()
+    r0, r1 = rel(pc[0], g["fwd1384_cond"]), rel(pc[1], g["fwd1384_null"])
+    print(f"fp32 forward n=1384: rel-L2 {r0:.2e} / {r1:.2e}")
+    assert r0 < FP32_MEL_REL and r1 < FP32_MEL_REL
+    del m32
+    torch.cuda.empty_cache()

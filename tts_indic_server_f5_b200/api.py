@@ -133,17 +133,23 @@ class CFM:
     @torch.inference_mode()
     def sample(self, cond, text, duration, *, lens=None, steps=32, cfg_strength=1.0, sway_sampling_coef=None, seed=None,
                max_duration=4096, vocoder=None, no_ref_audio=False, duplicate_test=False, t_inter=0.1, edit_mask=None,
-               y0=None):
+               y0=None, return_trajectory: bool = False):
         """Signature and return convention of the reference `CFM.sample` (cfm.py:82-99, :210): returns
         `(out [b, n, 100], trajectory)`.  Each utterance is sampled with batch-1 semantics (what the server computes);
-        rows past an utterance's own duration are zero.  `trajectory` holds only the final state ([1, b, n, 100]): the
-        33-state history the reference keeps is never consumed on the served path.  `y0` (list of [n_i, 100] or
-        [b, n, 100]) overrides the noise draw."""
+        rows past an utterance's own duration are zero.  By default `trajectory` holds only the final state ([1, b, n, 100]):
+        the 33-state history the reference keeps (cfm.py:200) is never consumed on the served path; `return_trajectory=True`
+        returns all `steps + 1` states ([steps + 1, b, n, 100], eager launches).  `y0` (list of [n_i, 100] or [b, n, 100])
+        overrides the noise draw."""
         if duplicate_test:
             raise NotImplementedError("duplicate_test is a training-time probe, not part of the served path")
         utts = self._prepare(cond, text, duration, lens, seed, max_duration, edit_mask, y0)
+        states: list = []
+
+        def keep(k, ws_):                                            # odeint's stacked states (cfm.py:200), before the prompt re-insert
+            states.append(ws_.x[:, : self.num_channels].clone())
+
         ws, layout = self.engine.sample_packed(utts, steps=steps, cfg_strength=cfg_strength,
-                                               sway_sampling_coef=sway_sampling_coef)
+                                               sway_sampling_coef=sway_sampling_coef, on_state=keep if return_trajectory else None)
         n_max = max(layout.lengths)
         out = torch.zeros(len(utts), n_max, self.num_channels, device=self._device, dtype=torch.float32)
         for i, (s, n) in enumerate(zip(layout.starts, layout.lengths)):
@@ -153,6 +159,11 @@ class CFM:
                     ws.cond_flag[s:s + utts[i].cond_len, None].bool(), torch.zeros_like(out[i, : utts[i].cond_len]),
                     out[i, : utts[i].cond_len])
         trajectory = out.unsqueeze(0)
+        if return_trajectory:
+            trajectory = torch.zeros(len(states), len(utts), n_max, self.num_channels, device=self._device, dtype=torch.float32)
+            for k, xs in enumerate(states):
+                for i, (s0, n) in enumerate(zip(layout.starts, layout.lengths)):
+                    trajectory[k, i, :n] = xs[s0:s0 + n]
         if vocoder is not None:
             out = vocoder(out.permute(0, 2, 1))
         return out, trajectory

@@ -477,8 +477,11 @@ class F5Engine:
         return ws, layout
 
     @torch.inference_mode()
-    def compute(self, ws: Workspace, steps: int = 32, cfg_strength: float = 2.0, generation: int | None = None) -> None:
-        """Device-resident hot path on a staged batch: hoisted work, the Euler loop, prompt re-insert (cfm.py:160-204)."""
+    def compute(self, ws: Workspace, steps: int = 32, cfg_strength: float = 2.0, generation: int | None = None,
+                on_state=None) -> None:
+        """Device-resident hot path on a staged batch: hoisted work, the Euler loop, prompt re-insert (cfm.py:160-204).
+        `on_state(k, ws)` is called with the ODE state after k = 0 .. steps Euler steps (the reference's trajectory,
+        cfm.py:200); it forces eager launches (the served path never asks for it and replays the step graph)."""
         if cfg_strength < 1e-5:
             raise NotImplementedError("cfg_strength < 1e-5 (single-branch sampling, cfm.py:170-171) is not on the served path")
         # Programmatic dependent launch pays where kernels are short (a single request: 5120 graph nodes of ~10 us, -3 % latency);
@@ -491,14 +494,20 @@ class F5Engine:
                                "workspace before it ran (stage -> run must not interleave with another stage of the same size)")
         ws.x.copy_(ws.x0)
         self.hoist(ws, steps)
-        self.run_steps(ws, steps, cfg_strength)
+        if on_state is None:
+            self.run_steps(ws, steps, cfg_strength)
+        else:
+            on_state(0, ws)
+            for s in range(steps):
+                self.step(ws, s, cfg_strength)
+                on_state(s + 1, ws)
         ops.where_rows(ws.x, ws.cond, ws.cond_flag, self.cfg.mel_dim)        # cfm.py:204
 
     def sample_packed(self, utts: list[UtteranceInput], steps: int = 32, cfg_strength: float = 2.0,
-                      sway_sampling_coef: float | None = -1.0) -> tuple[Workspace, PackedLayout]:
+                      sway_sampling_coef: float | None = -1.0, on_state=None) -> tuple[Workspace, PackedLayout]:
         """Run the sampler for a batch; the result stays on the device in `ws.x` (rows per `layout`)."""
         ws, layout = self.stage(utts, steps, sway_sampling_coef)
-        self.compute(ws, steps, cfg_strength)
+        self.compute(ws, steps, cfg_strength, on_state=on_state)
         return ws, layout
 
     @torch.inference_mode()
