@@ -1,7 +1,8 @@
 """ORACLE — test infrastructure only.  CPU fp32 restatement of the reference's F5-TTS inference path.
 
-Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s `cpu_baseline` / `--impl reference` legs may
-import this module; the product (`tts_indic_server_f5_b200/`) never does.
+Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s baseline legs (`cpu_baseline`, `--impl reference`, and the
+same-box torch-eager `gpu_eager_baseline` VERDICT r01 asked for) may import this module — as the checker or as the thing a
+baseline times, never as part of the product; `tts_indic_server_f5_b200/` never imports it.
 
 Each function follows the reference file:line it cites (paths relative to
 `/root/reference/src/server/f5_tts/`).  Three pieces of arithmetic live in third-party packages that are
@@ -10,7 +11,7 @@ algorithms and are "parity unpinned" by any reference test (the reference has no
   * x-transformers==2.2.8  RotaryEmbedding / apply_rotary_pos_emb   (call sites model/modules.py:418-419)
   * torchdiffeq==0.2.5     odeint(method="euler")                   (call site  model/cfm.py:200)
   * vocos==0.1.0           VocosBackbone + ISTFTHead                (call site  infer/utils_infer.py:472)
-Everything that IS in the tree (CFM.sample, DiT, modules) is pinned by `tests/test_oracle_vs_reference.py`,
+Everything that IS in the tree (CFM.sample, DiT, modules) is pinned by `tests/test_oracle_golden.py::test_oracle_vs_real_reference_modules`,
 which imports the real reference modules in place (through `oracle/ref_shims.py`) when `/root/reference`
 exists, and by the golden vectors under `tests/golden/` generated from the real reference by
 `oracle/make_golden.py`.

@@ -3,7 +3,7 @@
 Runs only where `/root/reference` exists (the build container); nothing that runs on the GPU box
 (`-m gpu` tests, `smoke()`, `bench.py`) may call `load_reference()`.  It is used to
   (a) validate `oracle/f5_oracle.py` against the reference's own modules on identical weights/inputs
-      (`tests/test_oracle_vs_reference.py`), and
+      (`tests/test_oracle_golden.py::test_oracle_vs_real_reference_modules`), and
   (b) mint the golden vectors committed under `tests/golden/` (`oracle/make_golden.py`).
 
 The reference imports nine packages that are not installed here.  Six are irrelevant to the arithmetic

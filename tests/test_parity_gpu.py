@@ -529,3 +529,29 @@ def test_trajectory_and_fp32_forward_at_c2_length(tiny_models, golden_dir):
     assert r0 < FP32_MEL_REL and r1 < FP32_MEL_REL
     del m32
     torch.cuda.empty_cache()
+
+
+def test_continuous_scheduler_on_the_engine(tiny_models):
+    """The serving loop with the real engine: requests submitted from several threads come back through futures and equal
+    `infer_process(seed=...)` per request bit for bit (the worker thread packs whatever is waiting into shared batches)."""
+    import threading
+    *_, model, voc = tiny_models
+    audio = S.prompt_audio(2.0, 5)
+    ref_text = T.finish_ref_text(T.synthetic_indic_text(30, 1, "kannada"))
+    texts = [T.synthetic_indic_text(40 + 7 * k, 50 + k, "kannada" if k % 2 else "devanagari") for k in range(5)]
+    cs = api.ContinuousScheduler(api.Synthesizer(model, voc), max_queue=16, max_batch_requests=8, max_wait_ms=50.0, nfe_step=6)
+    futs = {}
+
+    def client(k):
+        futs[k] = cs.submit((audio, 24000), ref_text, texts[k], seed=300 + k)
+
+    ths = [threading.Thread(target=client, args=(k,)) for k in range(5)]
+    [t.start() for t in ths]
+    [t.join() for t in ths]
+    got = {k: f.result(timeout=120) for k, f in futs.items()}
+    cs.close()
+    assert sum(cs.batches) == 5 and len(cs.batches) <= 3
+    for k in range(5):
+        wave, sr, mel = api.infer_process((audio, 24000), ref_text, texts[k], model, voc, nfe_step=6, seed=300 + k)
+        np.testing.assert_array_equal(got[k][0], wave)
+        np.testing.assert_array_equal(got[k][2], mel)

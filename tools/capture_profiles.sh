@@ -3,7 +3,7 @@
 #   launches_<tag>.csv       ncu launch list (gpu__time_duration.sum) of `python bench.py --steps 1 --warmup 3 --no-cpu-baseline`
 #   prof_<tag>_layer.ncu-rep ncu --set full of one DiT layer's kernels at C2 scale (tools/ncu_kernels.py)
 # Each command first runs WITHOUT ncu and must exit 0.
-TAG=${1:-r01b}
+TAG=${1:-r02}
 mkdir -p gpurun_out
 set -x
 timeout 300 python tools/ncu_kernels.py > gpurun_out/ncu_plain_$TAG.log 2>&1 || exit 1

@@ -173,6 +173,9 @@ class ContinuousScheduler:
     def _loop(self) -> None:
         import queue
         import time
+        dev = getattr(self._sched.syn, "device", None)
+        if dev is not None and getattr(dev, "type", None) == "cuda":
+            torch.cuda.set_device(dev)               # the current device is per thread: this worker owns the engine's GPU
         while not self._stop.is_set():
             try:
                 first = self._q.get(timeout=0.05)
