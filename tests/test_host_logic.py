@@ -434,3 +434,13 @@ def test_out_of_line_wait_fits_the_low_register_warps():
             assert top < budget, f"{fn}: out-of-line wait uses R{top}, the calling warp has {budget} registers"
             checked += 1
     assert checked >= 7
+
+
+def test_tile_width_rule():
+    """ops.pick_block_n: 256 for a full batch always; 128 where 256-wide tiles leave whole waves of the 148 SMs idle (a single
+    request: M = 1792 -> 56 tiles for N = 1024, two waves for QKV) — DESIGN.md §7, profiles/r02_launches_c1.csv."""
+    from tts_indic_server_f5_b200 import ops
+    for M in (158976, 98816, 40000):
+        assert [ops.pick_block_n(N, M) for N in (1024, 2048, 3072, 512)] == [256] * 4
+    assert ops.pick_block_n(1024, 1792) == 128 and ops.pick_block_n(3072, 1792) == 128 and ops.pick_block_n(2048, 1792) == 256
+    assert ops.pick_block_n(1032, 1792) == 128 and ops.pick_block_n(104, 1792) == 64 and ops.pick_block_n(1024) == 256
