@@ -195,6 +195,13 @@ int f5_diag_enable(void* mapped);
  * the reference launches ~40 torch kernels per DiT block with full stream serialization (model/modules.py:558-572). */
 int f5_set_pdl(int enabled);
 
+/* Kernel variants of the two Vocos-side memory kernels (A/B measurements; results agree to float round-off).  v outside the
+ * valid range only queries.  Both return the previous setting.  f5_dwconv7_ln: 3 = channel-split, window + taps in registers
+ * (default), 2 = one warp per run of rows, 1 = one warp per row.  f5_istft_frames: 2 = real-input 512-point form (default),
+ * 1 = 1024-point complex FFT.  Environment F5_DWCONV_V / F5_ISTFT_V set them at load. */
+int f5_set_dwconv7_variant(int v);
+int f5_set_istft_variant(int v);
+
 /* Library / device info. */
 int f5_device_check(void);      /* 0 if the current device is sm_100 */
 const char* f5_version(void);

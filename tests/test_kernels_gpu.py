@@ -327,7 +327,88 @@ def test_layernorm_mod():
         check(f"ln_affine D={D}", y, F.layer_norm(x, (D,), a, b, eps=1e-6), rel=4e-3)
 
 
-def test_dwconv7_ln():
+class _variant:
+    """Select a kernel variant through the C-ABI setter for the duration of a block (A/B forms of the same op)."""
+
+    def __init__(self, setter: str, v: int):
+        self.setter, self.v = setter, v
+
+    def __enter__(self):
+        from tts_indic_server_f5_b200 import _lib
+        self.old = getattr(_lib.lib, self.setter)(self.v)
+        assert getattr(_lib.lib, self.setter)(0) == self.v          # out-of-range argument: query only
+
+    def __exit__(self, *a):
+        from tts_indic_server_f5_b200 import _lib
+        getattr(_lib.lib, self.setter)(self.old)
+
+
+@pytest.mark.parametrize("variant", [3, 2, 1])
+def test_dwconv7_ln(variant):
+    with _variant("f5_set_dwconv7_variant", variant):
+        _dwconv7_ln_case()
+
+
+def _ragged_pos(lens, gaps, M=None):
+    """row_pos of utterances of `lens` rows separated by `gaps[i]` dead rows (gaps has one more entry than lens)."""
+    pos, starts = [], []
+    for g, n in zip(gaps, lens):
+        pos += [-1] * g
+        starts.append(len(pos))
+        pos += list(range(n))
+    pos += [-1] * gaps[-1]
+    if M is not None:
+        pos += [-1] * (M - len(pos))
+    return torch.tensor(pos, dtype=torch.int32), starts
+
+
+@pytest.mark.parametrize("C", [512, 256])
+def test_dwconv7_ln_variants_agree_on_a_ragged_pack(C):
+    """The three forms of f5_dwconv7_ln on a pack that exercises every window case: gaps of 1 and 2 rows (a +-3 window then
+    spans two utterances: only the key / position test keeps them apart), an utterance of a single row, utterances that start
+    at row 0 / end at the last row, run boundaries inside utterances.  Form 2 repeats form 1's operation order (bit-identical);
+    form 3 combines per-warp LayerNorm statistics (Chan) and may differ by one bf16 rounding.  All against torch."""
+    lens = [1, 37, 2, 701, 3, 1500, 64, 5, 333, 4097]
+    gaps = [0, 1, 2, 1, 8, 3, 1, 16, 2, 1, 0]
+    pos, starts = _ragged_pos(lens, gaps)
+    M = pos.numel()
+    pos = pos.to(DEV)
+    x = rnd(M, C, seed=143) * 3 + 0.5
+    x[pos < 0] = float("nan")                      # dead rows must never be read into a live output
+    w, bias, lw, lb = rnd(C, 7, seed=144, scale=0.4), rnd(C, seed=145), rnd(C, seed=146) + 1, rnd(C, seed=147)
+    outs = {}
+    for v in (1, 2, 3):
+        y = torch.full((M, C), 9.0, device=DEV, dtype=torch.bfloat16)
+        with _variant("f5_set_dwconv7_variant", v):
+            ops.dwconv7_ln(x, y, pos, w, bias, lw, lb)
+        torch.cuda.synchronize()
+        assert torch.isfinite(y.float()).all(), f"variant {v}: a dead row leaked"
+        assert y[pos < 0].abs().max().item() == 0
+        outs[v] = y
+    for s0, n in zip(starts, lens):
+        h = F.conv1d(x[s0:s0 + n].t()[None], w[:, None, :], bias, padding=3, groups=C)[0].t()
+        ref = F.layer_norm(h, (C,), lw, lb, eps=1e-6)
+        for v in (1, 2, 3):
+            check(f"dwconv7_ln v{v} C={C} n={n}", outs[v][s0:s0 + n], ref, rel=4e-3)
+    assert torch.equal(outs[2], outs[1])
+    d = (outs[3].float() - outs[1].float()).abs()
+    assert (d <= outs[1].float().abs() * 2 ** -7 + 4e-6).all()      # at most one bf16 ulp (+ fp32 round-off where the value is ~0)
+    assert (d > 0).float().mean().item() < 0.02
+    # split-operand (fp32 mode) planes: hi + lo carries 16 mantissa bits
+    planes = {}
+    for v in (1, 2, 3):
+        y = torch.full((M, 2 * C), 9.0, device=DEV, dtype=torch.bfloat16)
+        with _variant("f5_set_dwconv7_variant", v):
+            ops.dwconv7_ln(x, y, pos, w, bias, lw, lb, lo_off=C)
+        torch.cuda.synchronize()
+        planes[v] = y[:, :C].float() + y[:, C:].float()
+        assert y[pos < 0].abs().max().item() == 0
+    assert torch.equal(planes[2], planes[1])
+    live = pos >= 0
+    check(f"dwconv7_ln planes v3 vs v1 C={C}", planes[3][live], planes[1][live], rel=2e-5)
+
+
+def _dwconv7_ln_case():
     for C in (128, 512):
         n1, n2, gap = 100, 57, 5
         M = gap + n1 + gap + n2 + gap
@@ -428,7 +509,37 @@ def test_cfg_euler():
     assert torch.equal(xb[:half], wb.to(torch.bfloat16)) and torch.equal(xb[half:], wb.to(torch.bfloat16))
 
 
-def test_istft_vs_torch():
+@pytest.mark.parametrize("variant", [2, 1])
+def test_istft_vs_torch(variant):
+    with _variant("f5_set_istft_variant", variant):
+        _istft_vs_torch_case()
+
+
+@pytest.mark.parametrize("rows", [1, 2, 7, 1001])
+def test_istft_frames_variants_agree(rows):
+    """Windowed frames of the real-input form (512-point FFT, two frames per warp, MUFU sin / cos / ex2) against the first
+    kernel (1024-point complex FFT, sincosf / expf) and against torch.fft.irfft: odd and even frame counts (the last pair has
+    one frame), phases well outside [-pi, pi], clipped and tiny magnitudes."""
+    spec = rnd(rows, 1152, seed=259)
+    spec[:, :513] = spec[:, :513] * 2.5 - 0.5          # log-magnitudes: exp() from ~1e-4 to the 1e2 clip
+    spec[:, 513:1026] *= 25.0                          # phases up to +-100 rad
+    window = torch.hann_window(1024, device=DEV)
+    fr = {}
+    for v in (1, 2):
+        fr[v] = torch.full((rows, 1024), 7.0, device=DEV)
+        with _variant("f5_set_istft_variant", v):
+            ops.call("f5_istft_frames", ops.ptr(spec), spec.stride(0), rows, ops.ptr(window), ops.ptr(fr[v]), ops.stream_ptr())
+    torch.cuda.synchronize()
+    mag = spec[:, :513].double().exp().clip(max=1e2)
+    ph = spec[:, 513:1026].double()
+    S = mag * (ph.cos() + 1j * ph.sin())
+    ref = (torch.fft.irfft(S, n=1024, dim=1) * window.double()).float()
+    check(f"istft_frames v1 rows={rows}", fr[1], ref, rel=2e-5)
+    check(f"istft_frames v2 rows={rows}", fr[2], ref, rel=2e-5)
+    check(f"istft_frames v2 vs v1 rows={rows}", fr[2], fr[1], rel=2e-5)
+
+
+def _istft_vs_torch_case():
     segs = [(2, 50), (60, 1), (70, 129)]
     rows = 210
     spec = rnd(rows, 1152, seed=59)

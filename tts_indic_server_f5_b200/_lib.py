@@ -18,7 +18,8 @@ F5_ACT_NONE, F5_ACT_GELU_TANH, F5_ACT_GELU_ERF, F5_ACT_MISH = 0, 1, 2, 3
 EXPORTS = [
     "f5_gemm_bf16", "f5_attention_d64", "f5_attention_f32", "f5_grn_sumsq_f32", "f5_grn_apply_f32", "f5_layernorm_mod", "f5_dwconv7_ln", "f5_grn_sumsq", "f5_grn_apply",
     "f5_text_gather_pos", "f5_pack_bf16", "f5_where_rows", "f5_cfg_euler", "f5_time_sinus", "f5_silu_bf16",
-    "f5_istft_frames", "f5_istft_ola", "f5_mel_frames", "f5_randn_rows", "f5_diag_enable", "f5_set_pdl", "f5_device_check", "f5_version",
+    "f5_istft_frames", "f5_istft_ola", "f5_mel_frames", "f5_randn_rows", "f5_diag_enable", "f5_set_pdl", "f5_set_dwconv7_variant", "f5_set_istft_variant",
+    "f5_device_check", "f5_version",
 ]
 
 
@@ -72,6 +73,8 @@ def _load() -> C.CDLL:
         "f5_randn_rows": [vp, i64, i32, i32, vp, vp, vp, vp],
         "f5_diag_enable": [vp],
         "f5_set_pdl": [i32],
+        "f5_set_dwconv7_variant": [i32],
+        "f5_set_istft_variant": [i32],
         "f5_device_check": [],
     }
     for name, args in sig.items():

@@ -3,6 +3,7 @@
 // reductions use warp shuffles (one warp per row), grids are sized from the row count.
 #include "f5_common.cuh"
 #include "../../include/f5_b200.h"
+#include <cstdlib>
 
 namespace f5 {
 
@@ -148,6 +149,251 @@ __global__ void __launch_bounds__(256) dwconv7_ln_kernel(const float* __restrict
         } else {
           yr[i * 32 + lane] = make_uint2(pack_bf16x2(o0, o1), pack_bf16x2(o2, o3));
         }
+      }
+    }
+  }
+}
+
+// v2: one warp walks a RUN of consecutive rows with the 7-row window in REGISTERS.  The first form reads every input row seven
+// times (once per output row that it is a tap of): HBM sees it once, but the L1 / shared-memory datapath carries 7 x 2 KB per
+// output row and that, not HBM, was the bound (2.0 TB/s = 31 % of the HBM peak).  Here a row is loaded once per run (plus 6
+// halo rows per run): the window is a ring of 7 register slots rotated by unrolling the row loop 7 times (slot indices are
+// compile-time), and the load of row r + 4 is issued right after tap 0 of row r has consumed the slot it replaces, two
+// iterations before its first use.  Same operation order as the first form (bias, taps 0..6, two-pass LN): bit-identical.
+template <int NV>  // C = NV * 128
+__global__ void __launch_bounds__(128, 3) dwconv7_ln_run_kernel(const float* __restrict__ x, long long ldx,
+                                                                __nv_bfloat16* __restrict__ y, long long ldy, int M,
+                                                                const int* __restrict__ row_pos, const float* __restrict__ w,
+                                                                const float* __restrict__ bias, const float* __restrict__ ln_w,
+                                                                const float* __restrict__ ln_b, float eps, int lo_off, int run_len) {
+  pdl_wait();
+  pdl_launch();
+  constexpr int C = NV * 128;
+  __shared__ float4 wT[7][NV * 32];
+  __shared__ float4 cb[NV * 32], lw[NV * 32], lb[NV * 32];
+  for (int c4 = threadIdx.x; c4 < NV * 32; c4 += blockDim.x) {
+#pragma unroll
+    for (int k = 0; k < 7; ++k)
+      wT[k][c4] = make_float4(w[(4 * c4 + 0) * 7 + k], w[(4 * c4 + 1) * 7 + k], w[(4 * c4 + 2) * 7 + k], w[(4 * c4 + 3) * 7 + k]);
+    cb[c4] = reinterpret_cast<const float4*>(bias)[c4];
+    lw[c4] = reinterpret_cast<const float4*>(ln_w)[c4];
+    lb[c4] = reinterpret_cast<const float4*>(ln_b)[c4];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int r0 = (blockIdx.x * 4 + warp) * run_len;
+  if (r0 >= M) return;
+  const int r1 = r0 + run_len < M ? r0 + run_len : M;
+  float4 win[7][NV];
+  int pw[7];
+  // row rr -> a window slot (data + its position; -1 = outside the matrix).  Gap rows are loaded like any other row (their
+  // contents never pass the position test below), so the data load does not wait for the position load.
+  auto load_row = [&](int rr, float4 (&dst)[NV], int& p) {
+    p = -1;
+    if (rr >= 0 && rr < M) {
+      p = row_pos[rr];
+      const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(rr) * ldx);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) dst[i] = xr[i * 32 + lane];
+    }
+  };
+#pragma unroll
+  for (int s = 0; s < 7; ++s) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) win[s][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    load_row(r0 - 3 + s, win[s], pw[s]);
+  }
+#pragma unroll 1
+  for (int base = r0; base < r1; base += 7) {
+#pragma unroll
+    for (int j = 0; j < 7; ++j) {            // at step j the slot (j + k) % 7 holds row + k - 3
+      const int row = base + j;
+      if (row < r1) {                        // warp-uniform
+        const int pos = pw[(j + 3) % 7];
+        uint2* yr = reinterpret_cast<uint2*>(y + static_cast<size_t>(row) * ldy);
+        uint2* yl = reinterpret_cast<uint2*>(y + static_cast<size_t>(row) * ldy + lo_off);   // low plane (split-operand mode)
+        if (pos < 0) {
+#pragma unroll
+          for (int i = 0; i < NV; ++i) {
+            yr[i * 32 + lane] = make_uint2(0, 0);
+            if (lo_off > 0) yl[i * 32 + lane] = make_uint2(0, 0);
+          }
+          load_row(row + 4, win[j % 7], pw[j % 7]);
+        } else {
+          float4 acc[NV];
+#pragma unroll
+          for (int i = 0; i < NV; ++i) acc[i] = cb[i * 32 + lane];
+#pragma unroll
+          for (int k = 0; k < 7; ++k) {
+            const int sl = (j + k) % 7;
+            if (pw[sl] >= 0 && pw[sl] == pos + k - 3) {   // same utterance, not a gap row (else: the conv's zero padding)
+#pragma unroll
+              for (int i = 0; i < NV; ++i) {
+                const float4 xv = win[sl][i];
+                const float4 wv = wT[k][i * 32 + lane];
+                acc[i].x = fmaf(xv.x, wv.x, acc[i].x);
+                acc[i].y = fmaf(xv.y, wv.y, acc[i].y);
+                acc[i].z = fmaf(xv.z, wv.z, acc[i].z);
+                acc[i].w = fmaf(xv.w, wv.w, acc[i].w);
+              }
+            }
+            if (k == 0) load_row(row + 4, win[j % 7], pw[j % 7]);   // the oldest slot is free: next step's newest row
+          }
+          float s = 0.f;
+#pragma unroll
+          for (int i = 0; i < NV; ++i) s += (acc[i].x + acc[i].y) + (acc[i].z + acc[i].w);
+          const float mean = warp_sum(s) * (1.f / C);
+          float q = 0.f;
+#pragma unroll
+          for (int i = 0; i < NV; ++i) {
+            const float d0 = acc[i].x - mean, d1 = acc[i].y - mean, d2 = acc[i].z - mean, d3 = acc[i].w - mean;
+            q += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+          }
+          const float rstd = rsqrtf(warp_sum(q) * (1.f / C) + eps);
+#pragma unroll
+          for (int i = 0; i < NV; ++i) {
+            const float4 a4 = lw[i * 32 + lane], b4 = lb[i * 32 + lane];
+            const float o0 = (acc[i].x - mean) * rstd * a4.x + b4.x, o1 = (acc[i].y - mean) * rstd * a4.y + b4.y;
+            const float o2 = (acc[i].z - mean) * rstd * a4.z + b4.z, o3 = (acc[i].w - mean) * rstd * a4.w + b4.w;
+            if (lo_off > 0) {
+              uint32_t h0, l0, h1, l1;
+              split_bf16x2(o0, o1, h0, l0);
+              split_bf16x2(o2, o3, h1, l1);
+              yr[i * 32 + lane] = make_uint2(h0, h1);
+              yl[i * 32 + lane] = make_uint2(l0, l1);
+            } else {
+              yr[i * 32 + lane] = make_uint2(pack_bf16x2(o0, o1), pack_bf16x2(o2, o3));
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+// v3: channel-split form.  Timing the two forms above against their LSU traffic shows what binds them: per output row the
+// shared-memory / L1 pipe (128 B/clk/SM) carries 52 LDS.128 of taps / bias / LN affine (26.6 KB) on top of the 7 x 2 KB of
+// input rows, 317 clk per row against the 130 clk the row's 3 KB of HBM traffic needs at 6.5 TB/s.  Here a warp owns 128
+// CHANNELS (one float4 per lane) of a run of rows, so its 7 taps, bias and LN affine are 40 REGISTERS for the whole run, the
+// row window is a ring of 14 float4 (rows r-3 .. r+10: every load is issued 8 rows before its first use) and nothing but the
+// input row (LDG.128) and the output (STG.64) touches the LSU.  The C / 128 warps of a CTA walk the same run; LayerNorm
+// combines their per-warp (mean, M2) with Chan's formula through a double-buffered 8-byte slot per warp and ONE __syncthreads
+// per row.  FMAs are packed (fma.rn.f32x2).
+template <int NW>  // C = NW * 128, NW warps per CTA
+__global__ void __launch_bounds__(NW * 32, 4) dwconv7_ln_cs_kernel(const float* __restrict__ x, long long ldx,
+                                                               __nv_bfloat16* __restrict__ y, long long ldy, int M,
+                                                               const int* __restrict__ row_pos, const float* __restrict__ w,
+                                                               const float* __restrict__ bias, const float* __restrict__ ln_w,
+                                                               const float* __restrict__ ln_b, float eps, int lo_off, int run_len) {
+  pdl_wait();
+  pdl_launch();
+  constexpr int C = NW * 128;
+  constexpr int RING = 14;
+  __shared__ float2 part[2][NW];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c4 = warp * 32 + lane;                       // this lane's float4 of channels
+  float4 wk[7];
+#pragma unroll
+  for (int k = 0; k < 7; ++k) wk[k] = make_float4(w[(4 * c4 + 0) * 7 + k], w[(4 * c4 + 1) * 7 + k], w[(4 * c4 + 2) * 7 + k], w[(4 * c4 + 3) * 7 + k]);
+  const float4 cbv = reinterpret_cast<const float4*>(bias)[c4];
+  const float4 lwv = reinterpret_cast<const float4*>(ln_w)[c4];
+  const float4 lbv = reinterpret_cast<const float4*>(ln_b)[c4];
+  const int r0 = blockIdx.x * run_len;                   // CTA-uniform
+  if (r0 >= M) return;
+  const int r1 = r0 + run_len < M ? r0 + run_len : M;
+  // A window slot = the row's float4 + its KEY: row_pos[rr] - rr for a live row (the same value for every row of one
+  // utterance), INT_MIN for gap rows and rows outside the matrix.  Tap k of output row `row` reads rr = row + k - 3 and is
+  // inside the utterance iff row_pos[rr] == row_pos[row] + k - 3, i.e. iff key(rr) == key(row); everything else is the
+  // conv's zero padding.  Gap rows are loaded like any other row (their contents never pass the key test).
+  constexpr int DEAD = -2147483647 - 1;
+  float4 win[RING];
+  int key[RING];
+#pragma unroll
+  for (int s = 0; s < RING; ++s) {
+    const int rr = r0 - 3 + s;
+    win[s] = make_float4(0.f, 0.f, 0.f, 0.f);
+    key[s] = DEAD;
+    if (rr >= 0 && rr < M) {
+      const int p = row_pos[rr];
+      key[s] = p >= 0 ? p - rr : DEAD;
+      win[s] = reinterpret_cast<const float4*>(x + static_cast<size_t>(rr) * ldx)[c4];
+    }
+  }
+  int rn = r0 - 3 + RING;                                 // the next row to load (>= 0), its data and position pointers
+  const float* xn = x + static_cast<size_t>(rn) * ldx + 4 * c4;
+  const int* pn = row_pos + rn;
+  __nv_bfloat16* yo = y + static_cast<size_t>(r0) * ldy + 4 * c4;
+  auto load_next = [&](float4& dst, int& kdst) {
+    kdst = DEAD;
+    if (rn < M) {
+      const int p = *pn;
+      dst = *reinterpret_cast<const float4*>(xn);
+      kdst = p >= 0 ? p - rn : DEAD;
+    }
+    ++rn;
+    ++pn;
+    xn += ldx;
+  };
+  int buf = 0;
+#pragma unroll 1
+  for (int base = r0; base < r1; base += RING) {
+#pragma unroll
+    for (int j = 0; j < RING; ++j) {                     // at step j the slot (j + k) % RING holds row + k - 3
+      if (base + j < r1) {                               // CTA-uniform
+        const int kc = key[(j + 3) % RING];              // CTA-uniform (a property of the row)
+        if (kc == DEAD) {
+          *reinterpret_cast<uint2*>(yo) = make_uint2(0, 0);
+          if (lo_off > 0) *reinterpret_cast<uint2*>(yo + lo_off) = make_uint2(0, 0);
+          load_next(win[j % RING], key[j % RING]);
+        } else {
+          float2 a01 = make_float2(cbv.x, cbv.y), a23 = make_float2(cbv.z, cbv.w);
+#pragma unroll
+          for (int k = 0; k < 7; ++k) {
+            const int sl = (j + k) % RING;
+            if (key[sl] == kc) {
+              a01 = ffma2(make_float2(win[sl].x, win[sl].y), make_float2(wk[k].x, wk[k].y), a01);
+              a23 = ffma2(make_float2(win[sl].z, win[sl].w), make_float2(wk[k].z, wk[k].w), a23);
+            }
+            if (k == 0) load_next(win[j % RING], key[j % RING]);   // the oldest slot is free: row + RING - 3 goes there
+          }
+          // this warp's 128 channels: mean and M2 = sum (v - mean)^2; then Chan's combination over the NW warps
+          const float mw = warp_sum((a01.x + a01.y) + (a23.x + a23.y)) * (1.f / 128.f);
+          const float d0 = a01.x - mw, d1 = a01.y - mw, d2 = a23.x - mw, d3 = a23.y - mw;
+          const float m2w = warp_sum((d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3));
+          float mean = mw, m2 = m2w;
+          if (NW > 1) {
+            if (lane == 0) part[buf][warp] = make_float2(mw, m2w);
+            __syncthreads();                             // one barrier per row: the slots alternate, see above
+            float2 pr[NW];
+            mean = 0.f;
+#pragma unroll
+            for (int i = 0; i < NW; ++i) {
+              pr[i] = part[buf][i];
+              mean += pr[i].x;
+            }
+            mean *= (1.f / NW);
+            m2 = 0.f;
+#pragma unroll
+            for (int i = 0; i < NW; ++i) {
+              const float dm = pr[i].x - mean;
+              m2 += pr[i].y + 128.f * dm * dm;
+            }
+            buf ^= 1;
+          }
+          const float rstd = rsqrtf(m2 * (1.f / C) + eps);
+          const float o0 = (a01.x - mean) * rstd * lwv.x + lbv.x, o1 = (a01.y - mean) * rstd * lwv.y + lbv.y;
+          const float o2 = (a23.x - mean) * rstd * lwv.z + lbv.z, o3 = (a23.y - mean) * rstd * lwv.w + lbv.w;
+          if (lo_off > 0) {
+            uint32_t h0, l0, h1, l1;
+            split_bf16x2(o0, o1, h0, l0);
+            split_bf16x2(o2, o3, h1, l1);
+            *reinterpret_cast<uint2*>(yo) = make_uint2(h0, h1);
+            *reinterpret_cast<uint2*>(yo + lo_off) = make_uint2(l0, l1);
+          } else {
+            *reinterpret_cast<uint2*>(yo) = make_uint2(pack_bf16x2(o0, o1), pack_bf16x2(o2, o3));
+          }
+        }
+        yo += ldy;
       }
     }
   }
@@ -493,15 +739,51 @@ extern "C" int f5_layernorm_mod(const float* x, int64_t ldx, void* y, int64_t ld
   return F5_LAUNCH_RC();
 }
 
+static int f5_dwconv7_variant = [] { const char* e = getenv("F5_DWCONV_V"); return (e != nullptr && e[0] >= '1' && e[0] <= '3') ? e[0] - '0' : 3; }();
+extern "C" int f5_set_dwconv7_variant(int v) {
+  const int old = f5_dwconv7_variant;
+  if (v >= 1 && v <= 3) f5_dwconv7_variant = v;
+  return old;
+}
+
 extern "C" int f5_dwconv7_ln(const float* x, int64_t ldx, void* y, int64_t ldy, int32_t M, int32_t C, const int32_t* row_pos,
                              const float* w, const float* bias, const float* ln_w, const float* ln_b, float eps,
                              int32_t lo_off, void* stream) {
   if (!x || !y || !row_pos || !w || !bias || !ln_w || !ln_b || M <= 0 || C % 128 != 0 || C > 512 || ldx % 4 != 0 || ldy % 4 != 0 ||
       lo_off < 0 || lo_off % 4 != 0)
     return F5_ERR_ARG;
+  __nv_bfloat16* yo = reinterpret_cast<__nv_bfloat16*>(y);
+  // Three forms (see the kernels): 3 = channel-split, window and taps in registers (default); 2 = one warp per row run, window
+  // in registers; 1 = one warp per row, halo through L1.  F5_DWCONV_V in the environment / f5_set_dwconv7_variant select one (A/B measurements).
+  const int variant = f5_dwconv7_variant;
+  if (variant == 3) {
+    // one CTA (C / 128 warps) per run of rows, 4 CTAs per SM resident; runs are a multiple of the 14-slot window ring
+    const int slots = kNumSMsB200 * 4;
+    int run = ((M + slots - 1) / slots + 13) / 14 * 14;
+    if (run < 14) run = 14;
+    const int grid3 = (M + run - 1) / run;
+    switch (C / 128) {
+#define F5_CASE(NW) case NW: f5_launch(dwconv7_ln_cs_kernel<NW>, dim3(grid3), dim3(NW * 32), 0, F5_STREAM(stream), x, ldx, yo, ldy, M, row_pos, w, bias, ln_w, ln_b, eps, lo_off, run); break;
+      F5_CASE(1) F5_CASE(2) F5_CASE(3) F5_CASE(4)
+#undef F5_CASE
+    }
+    return F5_LAUNCH_RC();
+  }
+  if (variant == 2) {
+    // one run per warp where there are enough rows (12 warps per SM resident), a multiple of 7 rows (the window rotation)
+    const int slots = kNumSMsB200 * 12;
+    int run = ((M + slots - 1) / slots + 6) / 7 * 7;
+    if (run < 7) run = 7;
+    const int grid2 = ((M + run - 1) / run + 3) / 4;
+    switch (C / 128) {
+#define F5_CASE(NV) case NV: f5_launch(dwconv7_ln_run_kernel<NV>, dim3(grid2), dim3(128), 0, F5_STREAM(stream), x, ldx, yo, ldy, M, row_pos, w, bias, ln_w, ln_b, eps, lo_off, run); break;
+      F5_CASE(1) F5_CASE(2) F5_CASE(3) F5_CASE(4)
+#undef F5_CASE
+    }
+    return F5_LAUNCH_RC();
+  }
   const int blocks = (M + DW_ROWS_PER_CTA - 1) / DW_ROWS_PER_CTA;
   const int grid = blocks < kNumSMsB200 * 8 ? blocks : kNumSMsB200 * 8;
-  __nv_bfloat16* yo = reinterpret_cast<__nv_bfloat16*>(y);
   switch (C / 128) {
 #define F5_CASE(NV) case NV: f5_launch(dwconv7_ln_kernel<NV>, dim3(grid), dim3(256), 0, F5_STREAM(stream), x, ldx, yo, ldy, M, row_pos, w, bias, ln_w, ln_b, eps, lo_off); break;
     F5_CASE(1) F5_CASE(2) F5_CASE(3) F5_CASE(4)

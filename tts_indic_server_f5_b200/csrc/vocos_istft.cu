@@ -5,6 +5,7 @@
 // (32 x 32 decomposition, one shared-memory transpose); the stage moves 4104 B in + 4096 B out per frame.
 #include "f5_common.cuh"
 #include "../../include/f5_b200.h"
+#include <cstdlib>
 
 namespace f5 {
 
@@ -121,6 +122,136 @@ __global__ void __launch_bounds__(ISTFT_WARPS * 32) istft_frames_kernel(const fl
   }
 }
 
+// ---------------------------------------------------------------------------------------------- v2: real-input form
+// The same transform with half the butterflies: x is real, so the 1024-point inverse real FFT is ONE 512-point complex
+// inverse FFT of  Z[k] = (X[k] + conj X[512-k]) + i w^k (X[k] - conj X[512-k]),  w = e^{2 pi i / 1024},  k < 512,  with
+// x[2m] = Re z[m], x[2m+1] = Im z[m].  512 = 32 (k1, lanes) x 16 (k2, registers):
+//   step 1, one frame at a time, lane = k1: X[k1 + 32 k2] from (log-magnitude, phase) with ex2 / sin / cos on the MUFU after an
+//     explicit Cody-Waite reduction of the phase to [-pi, pi] (abs. error 5e-7 on a unit phasor; sincosf's slow path and expf
+//     were a third of the first version's 4.8 k instructions), the partner bin X[512-k] by one shuffle from lane 32 - k1,
+//     16-point inverse DFT over k2 in registers, twiddle e^{2 pi i k1 n2 / 512}, into a per-warp shared-memory tile;
+//   step 2, TWO frames at a time, lane = (frame, n2): 32-point inverse DFT over k1 in registers; lane (f, n2) owns
+//     z[16 n1 + n2] = (x[32 n1 + 2 n2], x[32 n1 + 2 n2 + 1]): one 8-byte store per n1, 128 B contiguous per half-warp.
+// ~1.3 k instructions per frame instead of 4.8 k, 2 x 16 + 32 complex registers instead of 2 x 32.
+template <int NP>
+__device__ __forceinline__ void idft_regs(float2 (&v)[NP]) {   // radix-2 DIF like idft32_regs; output n in v[bit-reverse(n)]
+  constexpr int STAGES = NP == 32 ? 5 : 4;
+#pragma unroll
+  for (int s = 0; s < STAGES; ++s) {
+    const int half = (NP / 2) >> s;
+#pragma unroll
+    for (int g = 0; g < NP; g += 2 * half) {
+#pragma unroll
+      for (int j = 0; j < half; ++j) {
+        const float2 a = v[g + j], b = v[g + j + half];
+        v[g + j] = make_float2(a.x + b.x, a.y + b.y);
+        const float2 d = make_float2(a.x - b.x, a.y - b.y);
+        const int m = j * (16 / half);                       // twiddle e^{+2 pi i j / (2 half)} = W32^m
+        if (m == 0) v[g + j + half] = d;
+        else if (m == 8) v[g + j + half] = make_float2(-d.y, d.x);
+        else v[g + j + half] = cmul(d, kW32[m]);
+      }
+    }
+  }
+}
+__host__ __device__ constexpr int brev4(int i) { return ((i & 1) << 3) | ((i & 2) << 1) | ((i & 4) >> 1) | ((i & 8) >> 3); }
+
+// min(exp(m), 100) (cos p + i sin p)
+__device__ __forceinline__ float2 polar_fast(float m, float p) {
+  const float mag = fminf(fast_ex2(m * 1.4426950408889634f), 100.f);
+  const float j = rintf(p * 0.15915494309189535f);
+  float r = fmaf(-j, 6.28125f, p);                           // 2 pi = 6.28125 (exact product for |j| < 2^16) + 1.9353071795864769e-3
+  r = fmaf(-j, 1.9353071795864769e-3f, r);
+  return make_float2(mag * __cosf(r), mag * __sinf(r));
+}
+
+constexpr int ISTFT2_WARPS = 4;
+constexpr int ISTFT2_TILE = 32 * 17 + 16;   // words per frame tile: rows of 17 (conflict-free column writes); a warp's two tiles sit 16 banks apart
+__global__ void __launch_bounds__(ISTFT2_WARPS * 32, 4) istft_frames2_kernel(const float* __restrict__ spec, long long lds, int rows,
+                                                                            const float* __restrict__ window,
+                                                                            float* __restrict__ frames) {
+  pdl_wait();
+  pdl_launch();
+  __shared__ float tre[ISTFT2_WARPS][2][ISTFT2_TILE];
+  __shared__ float tim[ISTFT2_WARPS][2][ISTFT2_TILE];
+  __shared__ float2 wins[NFFT / 2];                          // (window[2 i], window[2 i + 1]) / 1024
+  __shared__ float2 twz[512], twt[512];                      // the two twiddle tables, [k2 or n2][lane]: conflict-free LDS.64
+  for (int i = threadIdx.x; i < NFFT / 2; i += blockDim.x)
+    wins[i] = make_float2(window[2 * i] * (1.f / NFFT), window[2 * i + 1] * (1.f / NFFT));
+  for (int i = threadIdx.x; i < 512; i += blockDim.x) {
+    float2 t;
+    sincospif(static_cast<float>(i) / 512.f, &t.y, &t.x);            // i = k1 + 32 k2 = k: w^k = e^{2 pi i k / 1024}
+    twz[i] = t;
+    sincospif(static_cast<float>((i & 31) * (i >> 5)) / 256.f, &t.y, &t.x);   // i = k1 + 32 n2: e^{2 pi i k1 n2 / 512}
+    twt[i] = t;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int src_lane = (32 - lane) & 31;
+  const int h2 = lane >> 4, n2s = lane & 15;                         // step 2: which of the two frames, which n2
+  const int pairs = (rows + 1) >> 1;
+  for (int pr = blockIdx.x * ISTFT2_WARPS + warp; pr < pairs; pr += gridDim.x * ISTFT2_WARPS) {
+#pragma unroll 1
+    for (int h = 0; h < 2; ++h) {
+      const int f = 2 * pr + h;
+      if (f >= rows) break;                                          // warp-uniform
+      const float* sp = spec + static_cast<size_t>(f) * lds;
+      float2 X[17];
+#pragma unroll
+      for (int k2 = 0; k2 < 16; ++k2) {
+        const int k = lane + 32 * k2;
+        X[k2] = polar_fast(sp[k], sp[NBINS + k]);
+      }
+      X[16] = make_float2(0.f, 0.f);
+      if (lane == 0) {
+        X[0].y = 0.f;                                                // irfft ignores Im of DC / Nyquist
+        X[16] = make_float2(polar_fast(sp[NFFT / 2], sp[NBINS + NFFT / 2]).x, 0.f);
+      }
+      float2 Z[16];
+#pragma unroll
+      for (int k2 = 0; k2 < 16; ++k2) {
+        // partner bin 512 - (k1 + 32 k2) = (32 - k1) + 32 (15 - k2): lane 32 - k1; lane 0: 32 (16 - k2), its own
+        const float ox = __shfl_sync(0xffffffffu, X[15 - k2].x, src_lane);
+        const float oy = __shfl_sync(0xffffffffu, X[15 - k2].y, src_lane);
+        const float2 own = X[16 - k2];
+        const float2 B = lane == 0 ? make_float2(own.x, -own.y) : make_float2(ox, -oy);
+        const float2 A = X[k2];
+        const float2 S = make_float2(A.x + B.x, A.y + B.y);
+        const float2 D = cmul(twz[32 * k2 + lane], make_float2(A.x - B.x, A.y - B.y));
+        Z[k2] = make_float2(S.x - D.y, S.y + D.x);                   // S + i D
+      }
+      idft_regs<16>(Z);                                              // over k2: n2 in Z[brev4(n2)]
+      float* re = tre[warp][h];
+      float* im = tim[warp][h];
+#pragma unroll
+      for (int n2 = 0; n2 < 16; ++n2) {
+        const float2 bv = n2 == 0 ? Z[0] : cmul(Z[brev4(n2)], twt[32 * n2 + lane]);
+        re[lane * 17 + n2] = bv.x;
+        im[lane * 17 + n2] = bv.y;
+      }
+    }
+    __syncwarp();
+    {
+      const float* re = tre[warp][h2];
+      const float* im = tim[warp][h2];
+      float2 v[32];
+#pragma unroll
+      for (int k1 = 0; k1 < 32; ++k1) v[k1] = make_float2(re[k1 * 17 + n2s], im[k1 * 17 + n2s]);
+      idft_regs<32>(v);                                              // over k1: z[16 n1 + n2] in v[brev5(n1)]
+      const int f = 2 * pr + h2;
+      if (f < rows) {
+        float2* o = reinterpret_cast<float2*>(frames + static_cast<size_t>(f) * NFFT);
+#pragma unroll
+        for (int n1 = 0; n1 < 32; ++n1) {
+          const float2 wv = wins[16 * n1 + n2s];
+          o[16 * n1 + n2s] = make_float2(v[brev5(n1)].x * wv.x, v[brev5(n1)].y * wv.y);
+        }
+      }
+    }
+    __syncwarp();                                                    // the tiles are rewritten by the next pair
+  }
+}
+
 // grid (ceil(max_wav_len / 256), num_segs); seg = {row0, frames, wav_offset, _}
 __global__ void __launch_bounds__(256) istft_ola_kernel(const float* __restrict__ frames, const float* __restrict__ window,
                                                         const int* __restrict__ seg, float* __restrict__ wav,
@@ -151,9 +282,24 @@ __global__ void __launch_bounds__(256) istft_ola_kernel(const float* __restrict_
 
 }  // namespace f5
 
+// 2 = real-input form (512-point complex FFT, two frames per warp; default), 1 = the first kernel (1024-point complex FFT).
+// F5_ISTFT_V in the environment / f5_set_istft_variant select one (A/B measurements).
+static int f5_istft_variant = [] { const char* e = getenv("F5_ISTFT_V"); return (e != nullptr && e[0] >= '1' && e[0] <= '2') ? e[0] - '0' : 2; }();
+extern "C" int f5_set_istft_variant(int v) {
+  const int old = f5_istft_variant;
+  if (v >= 1 && v <= 2) f5_istft_variant = v;
+  return old;
+}
+
 extern "C" int f5_istft_frames(const float* spec, int64_t lds, int32_t rows, const float* window, float* frames_out,
                                void* stream) {
   if (!spec || !window || !frames_out || rows <= 0 || lds < 2 * f5::NBINS) return F5_ERR_ARG;
+  if (f5_istft_variant == 2) {
+    const int blocks2 = ((rows + 1) / 2 + f5::ISTFT2_WARPS - 1) / f5::ISTFT2_WARPS;
+    const int grid2 = blocks2 < 148 * 8 ? blocks2 : 148 * 8;
+    f5::f5_launch(f5::istft_frames2_kernel, dim3(grid2), dim3(f5::ISTFT2_WARPS * 32), 0, reinterpret_cast<cudaStream_t>(stream), spec, lds, rows, window, frames_out);
+    return static_cast<int>(cudaGetLastError());
+  }
   const int blocks = (rows + f5::ISTFT_WARPS - 1) / f5::ISTFT_WARPS;
   const int grid = blocks < 148 * 6 ? blocks : 148 * 6;
   f5::f5_launch(f5::istft_frames_kernel, dim3(grid), dim3(f5::ISTFT_WARPS * 32), 0, reinterpret_cast<cudaStream_t>(stream), spec, lds, rows, window, frames_out);
