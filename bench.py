@@ -177,6 +177,57 @@ def gpu_eager_baseline(workload: str):
     return out
 
 
+def memory_kernel_rates(voc, dev, hbm_gbs: float) -> dict:
+    """The HBM-bound kernels of the path timed ALONE on benchmark-sized inputs (CUDA events, median of 7 launches after 2
+    warm-ups; inputs of 0.5 - 2 GB, far above the 126 MB L2): algorithmic bytes per launch / time, against the measured copy
+    bandwidth of MEASURED_PEAKS.json.  LayerNorm at the C2 step's shape; the two Vocos-side kernels at 64 x 4096 frames (C5)."""
+    import torch
+    from tts_indic_server_f5_b200 import ops
+
+    def med(fn):
+        ts = []
+        for it in range(9):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            if it >= 2:
+                ts.append(a.elapsed_time(b))
+        return sorted(ts)[len(ts) // 2]
+
+    out = {}
+
+    def rec(name, ms, nbytes, what):
+        gbs = nbytes / ms / 1e6
+        out[name] = {"us": ms * 1e3, "algorithmic_bytes": nbytes, "gbs": gbs, "frac_of_hbm_peak": gbs / hbm_gbs, "bytes": what}
+
+    g = torch.Generator(device=dev).manual_seed(11)
+    M, D = 158976, 1024
+    x = torch.randn(M, D, generator=g, device=dev)
+    y = torch.empty(M, D, device=dev, dtype=torch.bfloat16)
+    sc, sh = torch.randn(D, generator=g, device=dev), torch.randn(D, generator=g, device=dev)
+    rec("layernorm_mod", med(lambda: ops.layernorm_mod(x, y, sc, sh, 1.0)), M * D * 6, f"{M} rows x {D}: fp32 in + bf16 out")
+    del x, y
+    eng = voc.engine
+    _, Rv, pos, _, _ = eng.plan([4096] * 64)
+    pos = pos.to(dev)
+    C = eng.cfg.dim
+    x = torch.randn(Rv, C, generator=g, device=dev)
+    y = torch.empty(Rv, C, device=dev, dtype=torch.bfloat16)
+    blk = eng.blocks[0]
+    rec("dwconv7_ln", med(lambda: ops.dwconv7_ln(x, y, pos, blk["dw_w"], blk["dw_b"], blk["ln_w"], blk["ln_b"])), Rv * C * 6,
+        f"{Rv} rows x {C}: fp32 in + bf16 out")
+    del x, y
+    spec = torch.randn(Rv, 1152, generator=g, device=dev)
+    frames = torch.empty(Rv, 1024, device=dev)
+    rec("istft_frames", med(lambda: ops.call("f5_istft_frames", ops.ptr(spec), spec.stride(0), Rv, ops.ptr(eng.window), ops.ptr(frames),
+                                             ops.stream_ptr())), Rv * (4104 + 4096), f"{Rv} frames: 1026 fp32 in + 1024 fp32 out")
+    del spec, frames
+    torch.cuda.empty_cache()
+    return out
+
+
 def emit(line: dict) -> None:
     """The ONE JSON line goes to the real stdout; everything else the process prints (NCCL banners, library chatter)
     was re-routed to stderr at start-up."""
@@ -434,6 +485,10 @@ def main():
                         "unit": "Mframe/s"}
         del mel
         torch.cuda.empty_cache()
+        try:
+            extras["memory_kernels"] = memory_kernel_rates(voc, dev, peaks.get("hbm_gbs", 6551.0))
+        except Exception as e:                      # a secondary block never takes the headline line down with it
+            extras["memory_kernels"] = {"error": f"{type(e).__name__}: {e}"}
         extras["gpu_eager_baseline"] = gpu_eager_baseline(args.workload)
 
     cpu_baseline = None

@@ -196,8 +196,8 @@ int f5_diag_enable(void* mapped);
 int f5_set_pdl(int enabled);
 
 /* Kernel variants of the two Vocos-side memory kernels (A/B measurements; results agree to float round-off).  v outside the
- * valid range only queries.  Both return the previous setting.  f5_dwconv7_ln: 3 = channel-split, window + taps in registers
- * (default), 2 = one warp per run of rows, 1 = one warp per row.  f5_istft_frames: 2 = real-input 512-point form (default),
+ * valid range only queries.  Both return the previous setting.  f5_dwconv7_ln: 2 = one warp per run of rows, row window in
+ * registers (default; bit-identical to 1), 3 = channel-split with taps in registers too, 1 = one warp per row.  f5_istft_frames: 2 = real-input 512-point form (default),
  * 1 = 1024-point complex FFT.  Environment F5_DWCONV_V / F5_ISTFT_V set them at load. */
 int f5_set_dwconv7_variant(int v);
 int f5_set_istft_variant(int v);

@@ -154,12 +154,15 @@ __global__ void __launch_bounds__(256) dwconv7_ln_kernel(const float* __restrict
   }
 }
 
-// v2: one warp walks a RUN of consecutive rows with the 7-row window in REGISTERS.  The first form reads every input row seven
-// times (once per output row that it is a tap of): HBM sees it once, but the L1 / shared-memory datapath carries 7 x 2 KB per
-// output row and that, not HBM, was the bound (2.0 TB/s = 31 % of the HBM peak).  Here a row is loaded once per run (plus 6
-// halo rows per run): the window is a ring of 7 register slots rotated by unrolling the row loop 7 times (slot indices are
-// compile-time), and the load of row r + 4 is issued right after tap 0 of row r has consumed the slot it replaces, two
-// iterations before its first use.  Same operation order as the first form (bias, taps 0..6, two-pass LN): bit-identical.
+// v2 (default): one warp walks a RUN of consecutive rows with the 7-row window in REGISTERS.  The first form reads every input
+// row seven times (once per output row that it is a tap of): HBM sees it once, but the L1 / shared-memory datapath (128 B/clk
+// per SM) carries 28 LDG.128 of input + 40 LDS.128 of taps / bias / LN affine = 34 KB per output row, 272 clk against the
+// 130 clk the row's 3 KB of HBM traffic needs at 6.5 TB/s: it measured 2.0 TB/s = 31 % of the HBM peak.  Here a row is loaded
+// once per run (plus 6 halo rows per run): the window is a ring of 7 register slots rotated by unrolling the row loop 7 times
+// (slot indices are compile-time), and the load of row r + 4 is issued right after tap 0 of row r has consumed the slot it
+// replaces, two iterations before its first use.  Same operation order as the first form (bias, taps 0..6, two-pass LN):
+// bit-identical output.  Measured (262 k rows x 512, same box, profiles/r02_vocos_kernels_ab.txt): 400.6 -> 255.2 us =
+// 3.16 TB/s = 48 % of the HBM peak; what is left is the 40 LDS.128 per row (20 KB: 160 clk).
 template <int NV>  // C = NV * 128
 __global__ void __launch_bounds__(128, 3) dwconv7_ln_run_kernel(const float* __restrict__ x, long long ldx,
                                                                 __nv_bfloat16* __restrict__ y, long long ldy, int M,
@@ -271,14 +274,14 @@ __global__ void __launch_bounds__(128, 3) dwconv7_ln_run_kernel(const float* __r
   }
 }
 
-// v3: channel-split form.  Timing the two forms above against their LSU traffic shows what binds them: per output row the
-// shared-memory / L1 pipe (128 B/clk/SM) carries 52 LDS.128 of taps / bias / LN affine (26.6 KB) on top of the 7 x 2 KB of
-// input rows, 317 clk per row against the 130 clk the row's 3 KB of HBM traffic needs at 6.5 TB/s.  Here a warp owns 128
-// CHANNELS (one float4 per lane) of a run of rows, so its 7 taps, bias and LN affine are 40 REGISTERS for the whole run, the
-// row window is a ring of 14 float4 (rows r-3 .. r+10: every load is issued 8 rows before its first use) and nothing but the
-// input row (LDG.128) and the output (STG.64) touches the LSU.  The C / 128 warps of a CTA walk the same run; LayerNorm
-// combines their per-warp (mean, M2) with Chan's formula through a double-buffered 8-byte slot per warp and ONE __syncthreads
-// per row.  FMAs are packed (fma.rn.f32x2).
+// v3: channel-split form (kept for A/B; f5_set_dwconv7_variant(3)).  It removes the LDS traffic that bounds v2: a warp owns
+// 128 CHANNELS (one float4 per lane) of a run of rows, so its 7 taps, bias and LN affine are 40 REGISTERS for the whole run,
+// the row window is a ring of 14 float4 (rows r-3 .. r+10: every load is issued 8 rows before its first use) and nothing but
+// the input row (LDG.128) and the output (STG.64) touches the LSU.  The C / 128 warps of a CTA walk the same run; LayerNorm
+// combines their per-warp (mean, M2) exactly (M2 = sum of the groups' M2 + n (mean_g - mean)^2) through a double-buffered
+// 8-byte slot per warp and ONE __syncthreads per row.  FMAs are packed (fma.rn.f32x2).  Measured 294.0 us (2.75 TB/s, 42 %):
+// ~165 instructions per warp per row x 4 warps and a barrier + two shuffle reductions on every row's critical path make it
+// issue / latency bound below v2; results differ from v1 / v2 by at most one bf16 rounding (tested).
 template <int NW>  // C = NW * 128, NW warps per CTA
 __global__ void __launch_bounds__(NW * 32, 4) dwconv7_ln_cs_kernel(const float* __restrict__ x, long long ldx,
                                                                __nv_bfloat16* __restrict__ y, long long ldy, int M,
@@ -739,7 +742,7 @@ extern "C" int f5_layernorm_mod(const float* x, int64_t ldx, void* y, int64_t ld
   return F5_LAUNCH_RC();
 }
 
-static int f5_dwconv7_variant = [] { const char* e = getenv("F5_DWCONV_V"); return (e != nullptr && e[0] >= '1' && e[0] <= '3') ? e[0] - '0' : 3; }();
+static int f5_dwconv7_variant = [] { const char* e = getenv("F5_DWCONV_V"); return (e != nullptr && e[0] >= '1' && e[0] <= '3') ? e[0] - '0' : 2; }();
 extern "C" int f5_set_dwconv7_variant(int v) {
   const int old = f5_dwconv7_variant;
   if (v >= 1 && v <= 3) f5_dwconv7_variant = v;
@@ -753,8 +756,9 @@ extern "C" int f5_dwconv7_ln(const float* x, int64_t ldx, void* y, int64_t ldy, 
       lo_off < 0 || lo_off % 4 != 0)
     return F5_ERR_ARG;
   __nv_bfloat16* yo = reinterpret_cast<__nv_bfloat16*>(y);
-  // Three forms (see the kernels): 3 = channel-split, window and taps in registers (default); 2 = one warp per row run, window
-  // in registers; 1 = one warp per row, halo through L1.  F5_DWCONV_V in the environment / f5_set_dwconv7_variant select one (A/B measurements).
+  // Three forms (see the kernels): 2 = one warp per run of rows, window in registers (default: fastest, bit-identical to 1);
+  // 3 = channel-split, window and taps in registers; 1 = one warp per row, halo through L1.  F5_DWCONV_V in the environment /
+  // f5_set_dwconv7_variant select one (A/B measurements).
   const int variant = f5_dwconv7_variant;
   if (variant == 3) {
     // one CTA (C / 128 warps) per run of rows, 4 CTAs per SM resident; runs are a multiple of the 14-slot window ring
