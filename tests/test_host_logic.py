@@ -444,3 +444,100 @@ def test_tile_width_rule():
         assert [ops.pick_block_n(N, M) for N in (1024, 2048, 3072, 512)] == [256] * 4
     assert ops.pick_block_n(1024, 1792) == 128 and ops.pick_block_n(3072, 1792) == 128 and ops.pick_block_n(2048, 1792) == 256
     assert ops.pick_block_n(1032, 1792) == 128 and ops.pick_block_n(104, 1792) == 64 and ops.pick_block_n(1024) == 256
+
+
+def test_speech_route_mirrors_the_reference_and_batches_concurrent_requests(tmp_path):
+    """`server.create_app` against the reference's route behaviour (routes/speech.py:19-41,
+    utils/tts_utils.py:39-65): 503 while the model is not loaded, 400 for empty text / unknown voice / empty reference text,
+    audio/wav attachment with a 16-bit 24 kHz PCM body that decodes to the engine's samples, X-Response-Time header; and the part
+    the reference lacks: requests that arrive together are ONE engine batch.  CPU: a fake engine behind the real scheduler."""
+    import io
+    import threading
+    import time
+    import wave as wavmod
+    from fastapi.testclient import TestClient
+    from tts_indic_server_f5_b200 import api, server
+
+    class Prep:
+        def __init__(self, d):
+            self.duration = d
+
+    class FakeSyn:
+        device = None
+
+        def _prep(self, spec, speed, fixd):
+            return Prep(40 + len(spec.gen_text))
+
+        def generate(self, specs, nfe, cfg, sway, speed, fixd, return_mel=False):
+            time.sleep(0.15)
+            waves = [np.full(2400, 0.001 * len(s.gen_text), dtype=np.float32) for s in specs]
+            return waves, [np.zeros((100, 5), dtype=np.float32) for _ in specs]
+
+    class FakeModel:
+        output_int16, ema_model, vocoder = True, object(), object()
+
+        def __init__(self):
+            self.prompt_calls = 0
+
+        def _prompt(self, path, ref_text):
+            self.prompt_calls += 1
+            return (torch.zeros(1, 24000), 24000), ref_text
+
+    class FakeManager:
+        repo_id, failed_reason = "ai4bharat/IndicF5", None
+
+        def __init__(self):
+            self.model, self.loads = None, 0
+
+        def load(self):
+            self.loads += 1
+            self.model = FakeModel()
+
+    syn = FakeSyn()
+    orig = api._synthesizer_for
+    api._synthesizer_for = lambda m, v: syn
+    try:
+        mgr = FakeManager()
+        voices = {"KAN_F (Happy)": server.Voice(str(tmp_path / "kan.wav"), "ref text. ")}
+        with pytest.raises(ValueError):
+            server.create_app(mgr, voices, default_voice="nobody")
+        app = server.create_app(mgr, voices, max_wait_ms=60.0)
+        no_lifespan = TestClient(app)                                   # without the lifespan the model is not loaded yet
+        assert no_lifespan.post("/v1/audio/speech", json={"text": "x"}).status_code == 503
+        with TestClient(app) as client:                                 # lifespan: manager.load(), like main.py:37-57
+            assert mgr.loads == 1 and mgr.model
+            assert client.get("/v1/health").json()["status"] == "healthy"
+            assert client.post("/v1/audio/speech", json={"text": "   "}).status_code == 400
+            assert client.post("/v1/audio/speech", json={}).status_code == 422
+            r = client.post("/v1/audio/speech/voice", json={"text": "x", "ref_audio_name": "nobody"})
+            assert r.status_code == 400 and r.json()["detail"] == "Invalid reference audio name."
+            r = client.post("/v1/audio/speech/voice", json={"text": "x", "ref_audio_name": "KAN_F (Happy)", "ref_text": " "})
+            assert r.status_code == 400 and r.json()["detail"] == "Reference text cannot be empty."
+            r = client.post("/v1/audio/speech", json={"text": "abcde"})
+            assert r.status_code == 200 and r.headers["content-type"] == "audio/wav"
+            assert r.headers["content-disposition"] == "attachment; filename=synthesized_kannada_speech.wav"
+            assert float(r.headers["x-response-time"]) >= 0.1
+            with wavmod.open(io.BytesIO(r.content)) as w:
+                assert (w.getframerate(), w.getnchannels(), w.getsampwidth(), w.getnframes()) == (24000, 1, 2, 2400)
+                pcm = np.frombuffer(w.readframes(2400), dtype="<i2")
+            want = np.rint(np.float32(np.int16(0.005 * 32768)) / 32768.0 * 32767.0)
+            assert (pcm == want).all()
+            # six clients at once: the first is picked up alone or with company, the rest ride together (never six batches)
+            res = {}
+
+            def call(k):
+                res[k] = client.post("/v1/audio/speech", json={"text": "y" * (k + 1)})
+
+            ths = [threading.Thread(target=call, args=(k,)) for k in range(6)]
+            [t.start() for t in ths]
+            [t.join() for t in ths]
+            assert all(res[k].status_code == 200 for k in range(6))
+            for k in range(6):                                          # every caller got ITS text's audio
+                with wavmod.open(io.BytesIO(res[k].content)) as w:
+                    v = np.frombuffer(w.readframes(1), dtype="<i2")[0]
+                assert v == np.rint(np.float32(np.int16(0.001 * (k + 1) * 32768)) / 32768.0 * 32767.0)
+            batches = client.get("/v1/health").json()["batches"]
+            assert sum(batches) == 7 and len(batches) <= 4
+        assert mgr.model.prompt_calls == 7                              # the fake does not cache; INF5Model._prompt does (md5)
+    finally:
+        api._synthesizer_for = orig

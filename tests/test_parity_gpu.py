@@ -392,6 +392,63 @@ def test_tts_manager_load_and_synthesize_vs_oracle(tiny_models, tmp_path):
     assert np.array_equal(b1, mgr.synthesize(gen, path, ref_text))           # ... and repeatable under torch.manual_seed
 
 
+def test_speech_route_on_the_engine_equals_the_manager_call(tiny_models, tmp_path):
+    """SURVEY §8f row 4 end to end: `server.create_app` around a real `TTSManager` (tiny weights).  `POST /v1/audio/speech` goes
+    prompt cache -> ContinuousScheduler (worker thread owns the GPU) -> packed engine batch -> cross-fade -> int16 -> 16-bit PCM
+    WAV, and must carry exactly the samples `TTSManager.synthesize` (boundary #1, managers.py:82-85) returns for the same text
+    under the same torch seed; concurrent requests come back correct and batched."""
+    import io
+    import threading
+    import wave as wavmod
+    from fastapi.testclient import TestClient
+    from tts_indic_server_f5_b200 import server
+    cfg, vcfg, sd, vsd, _, _ = tiny_models
+    rate = 24000
+    pcm = np.concatenate([np.zeros(int(0.2 * rate)), S.prompt_audio(1.2, 3)[0].numpy(), np.zeros(int(0.3 * rate))])
+    path = str(tmp_path / "kan.wav")
+    with wavmod.open(path, "wb") as w:
+        w.setnchannels(1); w.setsampwidth(2); w.setframerate(rate)
+        w.writeframes(np.clip(np.round(pcm * 32767), -32768, 32767).astype("<i2").tobytes())
+    ref_text = T.synthetic_indic_text(24, 1)
+    texts = [". ".join(T.synthetic_indic_text(60, 40 + 7 * k + i) for i in range(6 + 4 * k)) + "." for k in range(3)]
+    mgr = api.TTSManager(state_dict=sd, vocoder_state_dict=vsd)
+    app = server.create_app(mgr, {"KAN_F (Happy)": server.Voice(path, ref_text)}, max_wait_ms=50.0)
+
+    def samples(resp):
+        assert resp.status_code == 200 and resp.headers["content-type"] == "audio/wav"
+        with wavmod.open(io.BytesIO(resp.content)) as w:
+            assert (w.getframerate(), w.getnchannels(), w.getsampwidth()) == (24000, 1, 2)
+            return np.frombuffer(w.readframes(w.getnframes()), dtype="<i2")
+
+    def as_wav_pcm(int16_audio):                                              # tts_utils.py:60-64: / 32768, then PCM_16
+        return np.rint(int16_audio.astype(np.float32) / 32768.0 * 32767.0).astype(np.int16)
+
+    with TestClient(app) as client:                                           # lifespan: mgr.load()
+        assert mgr.model and client.get("/v1/health").json()["status"] == "healthy"
+        want = []
+        for k, t in enumerate(texts):
+            torch.manual_seed(100 + k)
+            want.append(mgr.synthesize(t, ref_audio_path=path, ref_text=ref_text))
+        torch.manual_seed(100)
+        got0 = samples(client.post("/v1/audio/speech", json={"text": texts[0]}))
+        assert got0.shape == want[0].shape and np.array_equal(got0, as_wav_pcm(want[0]))
+        res = {}
+
+        def call(k):
+            res[k] = client.post("/v1/audio/speech", json={"text": texts[k]})
+
+        ths = [threading.Thread(target=call, args=(k,)) for k in range(3)]
+        [t.start() for t in ths]
+        [t.join() for t in ths]
+        for k in range(3):                                                    # fresh noise per request: same length, sane audio
+            g = samples(res[k])
+            assert g.shape == want[k].shape and np.abs(g.astype(np.int32)).max() > 0
+        batches = client.get("/v1/health").json()["batches"]
+        print(f"speech route: batches {batches}")
+        assert sum(batches) == 4                                              # (how they group is asserted on the CPU, test_host_logic.py)
+        assert client.post("/v1/audio/speech", json={"text": " "}).status_code == 400
+
+
 def test_checkpoint_file_loads_like_the_state_dict(tiny_models, tmp_path):
     """`load_model(ckpt_path=...)` on an EMA .safetensors / .pt file (utils_infer.py:195-213 key rules) builds the same engine
     as the in-memory state dict: bit-identical samples."""

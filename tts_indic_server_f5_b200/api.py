@@ -561,12 +561,17 @@ class TTSManager:
         try:
             return self.model(text, ref_audio_path=ref_audio_path, ref_text=ref_text)
         except RuntimeError as e:
-            if "CUDA error" in str(e) or "cudaError" in str(e):
-                from . import _lib
-                self.failed_reason = f"{str(e).splitlines()[0]}; watchdog record: {_lib.read_diag()}"
-                logger.error(f"TTS engine failed: {self.failed_reason}")
-                self.model = None
+            self.note_failure(e)
             raise
+
+    def note_failure(self, e: BaseException) -> None:
+        """A CUDA error is sticky for the process: drop the model and keep the watchdog's record (also called by the batching
+        route, `server.py`, whose requests reach the engine through the scheduler instead of `synthesize`)."""
+        if "CUDA error" in str(e) or "cudaError" in str(e):
+            from . import _lib
+            self.failed_reason = f"{str(e).splitlines()[0]}; watchdog record: {_lib.read_diag()}"
+            logger.error(f"TTS engine failed: {self.failed_reason}")
+            self.model = None
 
 
 def wav_response_bytes(audio: np.ndarray, sample_rate: int = target_sample_rate) -> "io.BytesIO":
