@@ -493,6 +493,7 @@ class INF5Model:
         self.output_int16 = output_int16
         self.noise_fn = None          # tests: callable (chunk index, frames) -> [frames, 100] noise; None: fresh device draw
         self._prompts: dict[str, tuple] = {}
+        self._prompts_lock = threading.Lock()     # the batching route conditions prompts on worker threads (server.py)
 
     def to(self, device):
         return self
@@ -501,16 +502,18 @@ class INF5Model:
         import hashlib
         with open(ref_audio_path, "rb") as f:
             key = hashlib.md5(f.read()).hexdigest() + "|" + ref_text
-        hit = self._prompts.get(key)
+        with self._prompts_lock:
+            hit = self._prompts.get(key)
         if hit is None:
             path, text = preprocess_ref_audio_text(ref_audio_path, ref_text, show_info=lambda *_: None)
             audio, sr = _load_audio(path)
             if path != os.fspath(ref_audio_path):
                 os.unlink(path)                                   # the reference leaks its temp file (delete=False, :284)
             hit = ((audio, sr), text)
-            if len(self._prompts) >= 64:
-                self._prompts.pop(next(iter(self._prompts)))
-            self._prompts[key] = hit
+            with self._prompts_lock:
+                if len(self._prompts) >= 64:
+                    self._prompts.pop(next(iter(self._prompts)))
+                self._prompts[key] = hit
         return hit
 
     def __call__(self, text: str, ref_audio_path: str, ref_text: str):
