@@ -118,6 +118,36 @@ def test_text_frontend_vs_reference():
     assert torch.equal(T.list_str_to_idx(toks, vocab), ref.model_utils.list_str_to_idx(toks, vocab))
 
 
+@pytest.mark.skipif(not R.reference_available(), reason="reference tree only exists in the build container")
+def test_chunk_text_randomised_vs_reference():
+    """`chunk_text` (utils_infer.py:61-88: sentence split on `; : , . ! ?` and their full-width forms, byte-length budget, the
+    single-byte-ending space rule) is pure Python in the reference: 300 seeded random texts mixing Kannada / Devanagari code
+    points, ASCII words, every delimiter and stray whitespace, at five budgets, must chunk identically."""
+    import random
+    ref = R.load_reference()
+    rnd = random.Random(7)
+    kan = [chr(c) for c in range(0x0C85, 0x0CB9)] + ["\u0ccd", "\u0cbe", "\u200c"]
+    dev = [chr(c) for c in range(0x0905, 0x0939)] + ["\u094d", "\u093e"]
+    delim = list(";:,.!?") + ["；", "：", "，", "。", "！", "？"]
+    for case in range(300):
+        parts = []
+        for _ in range(rnd.randint(1, 40)):
+            kind = rnd.random()
+            if kind < 0.45:
+                parts.append("".join(rnd.choice(kan) for _ in range(rnd.randint(1, 9))))
+            elif kind < 0.75:
+                parts.append("".join(rnd.choice(dev) for _ in range(rnd.randint(1, 9))))
+            elif kind < 0.9:
+                parts.append("".join(rnd.choice("abcXYZ019") for _ in range(rnd.randint(1, 6))))
+            else:
+                parts.append(rnd.choice(["", " ", "  ", "\n"]))
+            r = rnd.random()
+            parts.append(rnd.choice(delim) + rnd.choice(["", " ", "  "]) if r < 0.35 else (" " if r < 0.9 else ""))
+        text = "".join(parts)
+        for mc in (1, 17, 60, 135, 1000):
+            assert T.chunk_text(text, mc) == ref.utils_infer.chunk_text(text, mc), (case, mc, text)
+
+
 @pytest.mark.skipif(os.environ.get("F5_SKIP_SLOW") == "1", reason="~1 min of CPU")
 def test_oracle_full_size_forward_is_finite_and_param_count():
     """Architecture pin: 337.10 M parameters with the vendored 2545-entry vocab."""
