@@ -155,3 +155,27 @@ def test_oracle_full_size_forward_is_finite_and_param_count():
     sd = W.make_dit_state_dict(cfg, seed=0)
     n_params = sum(v.numel() for v in sd.values())
     assert abs(n_params - 337.10e6) < 0.02e6, n_params
+
+
+def test_vocos_architecture_pin():
+    """vocos 0.1.0 is not in the reference tree (parity unpinned), so what CAN be pinned is pinned: the published
+    size of `charactr/vocos-mel-24khz` (13.5 M parameters) and the state-dict layout its
+    `pytorch_model.bin` has (`backbone.embed`, `backbone.norm`, 8 x `backbone.convnext.{i}.{dwconv,norm,pwconv1,pwconv2,gamma}`,
+    `backbone.final_layer_norm`, `head.out`, `head.istft.window`), which is what `load_vocoder(local_path=...)` consumes
+    (utils_infer.py:104-114), plus the 26.99 MFLOP per frame the roofline uses."""
+    vc = W.VOCOS_24K
+    sd = W.make_vocos_state_dict(vc, seed=0)
+    n_params = sum(v.numel() for k, v in sd.items() if k != "head.istft.window")
+    assert n_params == 13_531_650
+    want = {"backbone.embed.weight": (512, 100, 7), "backbone.embed.bias": (512,), "backbone.norm.weight": (512,),
+            "backbone.norm.bias": (512,), "backbone.final_layer_norm.weight": (512,), "backbone.final_layer_norm.bias": (512,),
+            "head.out.weight": (1026, 512), "head.out.bias": (1026,), "head.istft.window": (1024,)}
+    for i in range(8):
+        p = f"backbone.convnext.{i}."
+        want.update({p + "dwconv.weight": (512, 1, 7), p + "dwconv.bias": (512,), p + "norm.weight": (512,), p + "norm.bias": (512,),
+                     p + "pwconv1.weight": (1536, 512), p + "pwconv1.bias": (1536,), p + "pwconv2.weight": (512, 1536),
+                     p + "pwconv2.bias": (512,), p + "gamma": (512,)})
+    assert {k: tuple(v.shape) for k, v in sd.items()} == want
+    assert torch.equal(sd["head.istft.window"], torch.hann_window(1024))
+    macs = 100 * 512 * 7 + 8 * (512 * 7 + 2 * 512 * 1536) + 512 * 1026          # embed + 8 blocks + head, per frame
+    assert abs(2 * macs - 26.99e6) < 0.01e6
