@@ -179,3 +179,38 @@ def test_vocos_architecture_pin():
     assert torch.equal(sd["head.istft.window"], torch.hann_window(1024))
     macs = 100 * 512 * 7 + 8 * (512 * 7 + 2 * 512 * 1536) + 512 * 1026          # embed + 8 blocks + head, per frame
     assert abs(2 * macs - 26.99e6) < 0.01e6
+
+
+def test_third_party_restatements_have_the_properties_of_what_they_restate():
+    """x-transformers RoPE and torchdiffeq Euler are not in the reference tree (parity unpinned); these are the properties any
+    faithful restatement must have, checked in float64 against INDEPENDENT formulations: RoPE on interleaved pairs is the complex
+    rotation (x0 + i x1) e^{i n theta_j} with theta_j = 10000^(-2j/64), it leaves channels >= 64 alone, and
+    q.k after rotation depends only on the position difference; fixed-grid Euler of y' = A y is the ordered product of
+    (I + dt_k A) and returns every grid state (Appendix A.2)."""
+    g = torch.Generator().manual_seed(3)
+    n, d = 37, 64
+    x = torch.randn(2, n, 80, generator=g)                                               # fp32, like the model's q / k
+    y = O.apply_rotary_pos_emb(x, O.rotary_freqs(n, d))
+    assert y.dtype == x.dtype and torch.equal(y[..., d:], x[..., d:])
+    theta = 10000.0 ** (-torch.arange(0, d, 2, dtype=torch.float64) / d)
+    ang = torch.arange(n, dtype=torch.float64)[:, None] * theta[None]                      # [n, 32]
+    xd = x.double()
+    z = torch.complex(xd[..., 0:d:2], xd[..., 1:d:2]) * torch.polar(torch.ones_like(ang), ang)
+    assert (y[..., 0:d:2] - z.real).abs().max() < 1e-5 and (y[..., 1:d:2] - z.imag).abs().max() < 1e-5   # fp32 math (A.1)
+    q, k = torch.randn(d, generator=g), torch.randn(d, generator=g)
+    big = O.rotary_freqs(64, d)[0]
+
+    def rot(v, pos):
+        return O.apply_rotary_pos_emb(v[None, None, :], big[None, pos:pos + 1])[0, 0]
+
+    dots = [float(rot(q, m) @ rot(k, m + 5)) for m in (0, 7, 31, 58)]
+    assert max(dots) - min(dots) < 1e-4 * max(1.0, abs(dots[0]))
+    A = torch.randn(4, 4, generator=g, dtype=torch.float64) * 0.3
+    y0 = torch.randn(4, generator=g, dtype=torch.float64)
+    t = O.sway_time_grid(8, -1.0, dtype=torch.float64)
+    ys = O.odeint_euler(lambda t0, yy: A @ yy, y0, t)
+    assert ys.shape == (9, 4) and torch.equal(ys[0], y0)
+    want = y0.clone()
+    for k_ in range(8):
+        want = (torch.eye(4, dtype=torch.float64) + (t[k_ + 1] - t[k_]) * A) @ want
+        assert (ys[k_ + 1] - want).abs().max() < 1e-12
