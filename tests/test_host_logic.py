@@ -541,3 +541,20 @@ def test_speech_route_mirrors_the_reference_and_batches_concurrent_requests(tmp_
         assert mgr.model.prompt_calls == 7                              # the fake does not cache; INF5Model._prompt does (md5)
     finally:
         api._synthesizer_for = orig
+
+
+def test_shard_plan_fuzz_covers_every_utterance_once():
+    """`dist.shard_plan` on 300 seeded random request batches, including the corners a server meets (no utterances, fewer
+    utterances than ranks, one 4096-frame utterance, tiny row budgets): every utterance lands on exactly one rank and in
+    exactly one pack of that rank; ranks without work get empty lists (SURVEY §8e partitioning)."""
+    import random
+    from tts_indic_server_f5_b200.dist import shard_plan
+    rnd = random.Random(0)
+    for _ in range(300):
+        n, w = rnd.randint(0, 40), rnd.choice([1, 2, 3, 4, 8])
+        lens = [rnd.randint(1, 4096) for _ in range(n)]
+        plan = shard_plan(lens, w, max_rows=rnd.choice([1024, 65536, 131072]))
+        assert len(plan["parts"]) == len(plan["packs"]) == w
+        assert sorted(i for part in plan["parts"] for i in part) == list(range(n))
+        for r in range(w):
+            assert sorted(j for pk in plan["packs"][r] for j in pk) == list(range(len(plan["parts"][r])))
