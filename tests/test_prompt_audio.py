@@ -136,3 +136,33 @@ def test_remove_silence_for_generated_wav(tmp_path):
     with wave.open(str(work), "rb") as w:
         got = w.readframes(w.getnframes())
     assert got == ref._data and len(got) < os.path.getsize(src) - 2 * rate * 2       # well over a second of pause removed
+
+
+def test_clip_reference_fuzz_matches_pydub_port(tmp_path):
+    """40 seeded random prompts (2 - 30 s; bursts and silences of random lengths from 20 ms to 7 s, noise floors either side
+    of the -50 / -42 dBFS thresholds, mono / stereo, four sample rates): the numpy implementation and the audioop restatement
+    of the pydub calls must agree byte for byte and print the same messages, with and without clipping."""
+    rng = np.random.default_rng(99)
+    for case in range(40):
+        rate = int(rng.choice([16000, 22050, 24000, 44100]))
+        ch = int(rng.choice([1, 1, 2]))
+        plan, total = [], 0.0
+        target = float(rng.uniform(2.0, 30.0))
+        while total < target:
+            sec = float(np.exp(rng.uniform(np.log(0.02), np.log(7.0))))
+            plan.append((sec, "v" if (len(plan) % 2 == int(case % 2)) else "s"))
+            total += sec
+        noise_db = float(rng.choice([-75.0, -55.0, -48.0, -44.0, -40.0]))
+        path = tmp_path / f"fuzz{case}.wav"
+        write_wav(path, synth(rate, plan, seed=1000 + case, channels=ch, noise_db=noise_db), rate, ch)
+        for clip in (True, False):
+            ma, mp = [], []
+            got = A.clip_reference(A.PcmSegment.from_wav(str(path)), clip, ma.append)
+            ref = P.clip_reference(P.Seg.from_wav(str(path)), clip, mp.append)
+            assert (got.frame_rate, got.channels, got.sample_width) == (ref.frame_rate, ref.channels, ref.sample_width), case
+            assert got.data.astype("<i2").tobytes() == ref._data, (case, clip, rate, ch, noise_db, plan)
+            assert ma == mp, (case, clip)
+        got = A.remove_silence_segment(A.PcmSegment.from_wav(str(path)))             # utils_infer.py:530-539 on the same file
+        ref = P.remove_silence_for_generated_wav_seg(P.Seg.from_wav(str(path)))
+        assert (got.frame_rate, got.channels, got.sample_width) == (ref.frame_rate, ref.channels, ref.sample_width), case
+        assert got.data.astype("<i2").tobytes() == ref._data, (case, "remove_sil")

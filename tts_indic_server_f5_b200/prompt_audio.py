@@ -266,7 +266,7 @@ def clip_reference(seg: PcmSegment, clip_short=True, show_info=print) -> PcmSegm
     """utils_infer.py:288-318: the <= 15 s clipping passes, edge trim and the 50 ms tail."""
     if clip_short:
         def gather(min_silence_len, silence_thresh, label):
-            out = seg.spawn(seg.data[:0])
+            out = PcmSegment.silent(0, 1, 2, 11025)      # AudioSegment.silent(duration=0): pydub's defaults; `+` lifts it to the source format
             for s in split_on_silence(seg, min_silence_len=min_silence_len, silence_thresh=silence_thresh, keep_silence=1000, seek_step=10):
                 if len(out) > 6000 and len(out + s) > 15000:
                     show_info(f"Audio is over 15s, clipping short. ({label})")
@@ -296,7 +296,7 @@ def preprocess_ref_audio(ref_audio_orig: str, clip_short=True, show_info=print) 
 def remove_silence_segment(seg: PcmSegment) -> PcmSegment:
     """utils_infer.py:530-539 on a segment: keep the non-silent stretches (>= 1 s below -50 dBFS counts as silence, 500 ms of it
     kept on each side) and join them."""
-    out = seg.spawn(seg.data[:0])
+    out = PcmSegment.silent(0, 1, 2, 11025)              # as above: a prompt with no non-silent stretch stays an empty 11 025 Hz segment
     for s in split_on_silence(seg, min_silence_len=1000, silence_thresh=-50, keep_silence=500, seek_step=10):
         out = out + s
     return out
