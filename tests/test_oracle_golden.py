@@ -214,3 +214,64 @@ def test_third_party_restatements_have_the_properties_of_what_they_restate():
     for k_ in range(8):
         want = (torch.eye(4, dtype=torch.float64) + (t[k_ + 1] - t[k_]) * A) @ want
         assert (ys[k_ + 1] - want).abs().max() < 1e-12
+
+
+@pytest.mark.skipif(not R.reference_available(), reason="reference tree only exists in the build container")
+def test_driver_host_logic_vs_the_real_infer_batch_process():
+    """Everything `infer_batch_process` (utils_infer.py:406-524) does AROUND `model.sample` / `vocoder.decode`, run through the
+    REAL reference function with recording stubs for the two model objects, against the product's host side (`Synthesizer._prep`,
+    the gain rule, `cross_fade`): mono mix, RMS boost of quiet prompts, torchaudio resample of non-24 kHz prompts, the
+    single-byte-ending space rule, tokens, `ref_audio_len`, the byte-ratio / fix_duration / speed duration rules, the prompt
+    strip, RMS un-scaling and the 0.15 s cross-fade of the chunk waves."""
+    from tts_indic_server_f5_b200 import api
+    from tts_indic_server_f5_b200.scheduler import cross_fade
+    ref = R.load_reference()
+
+    class StubModel:
+        def __init__(self):
+            self.calls = []
+
+        def sample(self, cond, text, duration, steps, cfg_strength, sway_sampling_coef):
+            self.calls.append(dict(cond=cond.clone(), text=text, duration=duration, steps=steps, cfg=cfg_strength, sway=sway_sampling_coef))
+            n = max(int(duration), cond.shape[-1] // 256 + 3)
+            return torch.randn(1, n, 100, generator=torch.Generator().manual_seed(len(self.calls))), None
+
+    class StubVocoder:
+        def decode(self, mel):
+            F_ = mel.shape[-1]
+            return torch.randn(1, 256 * (F_ - 1), generator=torch.Generator().manual_seed(F_)) * 0.1
+
+    g = torch.Generator().manual_seed(11)
+    cases = [   # (channels, rate, seconds, amplitude, ref_text, speed, fix_duration)
+        (1, 24000, 3.0, 0.3, T.synthetic_indic_text(30, 1) + ".", 1.0, None),        # ends in a 1-byte char: the space rule
+        (2, 16000, 2.2, 0.02, T.synthetic_indic_text(24, 2), 0.8, None),              # stereo, quiet (RMS boost), resampled
+        (1, 44100, 1.7, 0.5, T.synthetic_indic_text(20, 3) + ". ", 1.3, None),
+        (1, 24000, 2.5, 0.05, T.synthetic_indic_text(26, 4), 1.0, 9.5),               # fix_duration
+    ]
+    for ci, (ch, rate, sec, amp, ref_text, speed_, fixd) in enumerate(cases):
+        audio = torch.randn(ch, int(sec * rate), generator=g) * amp
+        chunks = [T.synthetic_indic_text(40 + 13 * k, 50 + 7 * ci + k) + "." for k in range(3)]
+        m, v = StubModel(), StubVocoder()
+        want_wave, want_sr, want_mel = ref.utils_infer.infer_batch_process((audio, rate), ref_text, chunks, m, v, speed=speed_,
+                                                                           fix_duration=fixd, device=None)
+        assert want_sr == 24000 and len(m.calls) == 3
+        waves = []
+        for k, (chunk, call) in enumerate(zip(chunks, m.calls)):
+            spec = S.UtteranceSpec(audio=audio, ref_text=ref_text, gen_text=chunk, duration=None, noise_index=k, meta={"sr": rate})
+            p = api.Synthesizer._prep(None, spec, speed_, fixd)
+            assert torch.equal(p.audio, call["cond"]), (ci, k)                   # mono mix, RMS boost, resample: same samples
+            assert p.tokens == call["text"][0] and p.duration == call["duration"], (ci, k)
+            assert p.ref_len == call["cond"].shape[-1] // 256
+            assert (call["steps"], call["cfg"], call["sway"]) == (api.nfe_step, api.cfg_strength, api.sway_sampling_coef)
+            # what the engine does after sampling: strip the prompt frames, vocode, undo the RMS boost (gain fused into the ISTFT)
+            n = max(p.duration, p.audio.shape[-1] // 256 + 3)
+            mel = torch.randn(1, n, 100, generator=torch.Generator().manual_seed(k + 1))[:, p.ref_len:, :].permute(0, 2, 1)
+            wave = v.decode(mel)
+            gain = p.rms / api.target_rms if p.rms < api.target_rms else 1.0
+            if gain != 1.0:
+                wave = wave * torch.tensor(gain, dtype=torch.float32)
+            waves.append(wave.squeeze().numpy())
+            assert np.array_equal(want_mel[:, sum(w_.shape[0] // 256 + 1 for w_ in waves[:-1]):][:, :mel.shape[-1]], mel[0].numpy())
+        got = cross_fade(waves, 0.15, 24000)
+        assert got.shape == want_wave.shape
+        np.testing.assert_allclose(got, want_wave, rtol=0, atol=2e-7)             # the gain is one fp32 multiply either way
