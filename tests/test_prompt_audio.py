@@ -166,3 +166,67 @@ def test_clip_reference_fuzz_matches_pydub_port(tmp_path):
         ref = P.remove_silence_for_generated_wav_seg(P.Seg.from_wav(str(path)))
         assert (got.frame_rate, got.channels, got.sample_width) == (ref.frame_rate, ref.channels, ref.sample_width), case
         assert got.data.astype("<i2").tobytes() == ref._data, (case, "remove_sil")
+
+
+def test_the_real_preprocess_ref_audio_text_on_the_port_primitives(tmp_path, monkeypatch):
+    """The REAL `preprocess_ref_audio_text` (utils_infer.py:282-351) executed in place, with `pydub.AudioSegment` / `pydub.silence`
+    bound to the audioop restatement of those primitives (oracle/pydub_port.py): its control flow — the two clipping passes, the
+    15 s cut, edge trim, 50 ms tail, WAV export, the '. ' rule on the reference text — then runs as written by the reference's
+    authors, and both restatements of it (`P.clip_reference`, the product's `api.preprocess_ref_audio_text`) must produce its
+    file, byte for byte, and its text, on every prompt of CASES plus ten random ones."""
+    from oracle import ref_shims as R
+    if not R.reference_available():
+        pytest.skip("reference tree only exists in the build container")
+    import types
+    from tts_indic_server_f5_b200 import api
+    ui = R.load_reference().utils_infer
+
+    def export(self, path, format="wav"):                       # pydub's export(format="wav") is the wave module on the raw data
+        assert format == "wav"
+        with wave.open(path, "wb") as w:
+            w.setnchannels(self.channels)
+            w.setsampwidth(self.sample_width)
+            w.setframerate(self.frame_rate)
+            w.writeframesraw(self._data)
+
+    monkeypatch.setattr(P.Seg, "from_file", classmethod(lambda cls, path: cls.from_wav(path)), raising=False)
+    monkeypatch.setattr(P.Seg, "export", export, raising=False)
+    monkeypatch.setattr(ui, "AudioSegment", P.Seg)
+    monkeypatch.setattr(ui, "silence", types.SimpleNamespace(split_on_silence=P.split_on_silence,
+                                                            detect_leading_silence=P.detect_leading_silence))
+    rng = np.random.default_rng(5)
+    cases = dict(CASES)
+    for k in range(10):
+        plan, total, target = [], 0.0, float(rng.uniform(2.0, 28.0))
+        while total < target:
+            sec = float(np.exp(rng.uniform(np.log(0.03), np.log(6.0))))
+            plan.append((sec, "v" if len(plan) % 2 == k % 2 else "s"))
+            total += sec
+        cases[f"rand{k}"] = (int(rng.choice([16000, 24000, 44100])), int(rng.choice([1, 2])), plan)
+    texts = ["ನಮಸ್ಕಾರ", "ನಮಸ್ಕಾರ.", "ನಮಸ್ಕಾರ. ", "नमस्ते。", "abc?"]
+    for i, (name, (rate, ch, plan)) in enumerate(sorted(cases.items())):
+        src = tmp_path / f"{name}.wav"
+        write_wav(src, synth(rate, plan, seed=200 + i, channels=ch), rate, ch)
+        ref_text = texts[i % len(texts)]
+        msgs_r, msgs_a = [], []
+        ref_path, ref_out_text = ui.preprocess_ref_audio_text(str(src), ref_text, show_info=msgs_r.append)
+        got_path, got_text = api.preprocess_ref_audio_text(str(src), ref_text, show_info=msgs_a.append)
+        port = P.clip_reference(P.Seg.from_wav(str(src)), True, lambda *_: None)
+        with wave.open(ref_path, "rb") as w:
+            want = (w.getframerate(), w.getnchannels(), w.getsampwidth(), w.readframes(w.getnframes()))
+        with wave.open(got_path, "rb") as w:
+            got = (w.getframerate(), w.getnchannels(), w.getsampwidth(), w.readframes(w.getnframes()))
+        os.unlink(ref_path)
+        os.unlink(got_path)
+        assert got == want, name
+        assert (port.frame_rate, port.channels, port.sample_width, port._data) == want, name
+        assert got_text == ref_out_text and msgs_a == msgs_r, name
+        # the real `remove_silence_for_generated_wav` (utils_infer.py:529-538) and the product's, in place on two copies
+        import shutil
+        ca, cb = tmp_path / f"{name}_a.wav", tmp_path / f"{name}_b.wav"
+        shutil.copy(src, ca)
+        shutil.copy(src, cb)
+        ui.remove_silence_for_generated_wav(str(ca))
+        A.remove_silence_for_generated_wav(str(cb))
+        with wave.open(str(ca), "rb") as wa, wave.open(str(cb), "rb") as wb:
+            assert wa.getparams()[:3] == wb.getparams()[:3] and wa.readframes(wa.getnframes()) == wb.readframes(wb.getnframes()), name
