@@ -275,3 +275,76 @@ def test_driver_host_logic_vs_the_real_infer_batch_process():
         got = cross_fade(waves, 0.15, 24000)
         assert got.shape == want_wave.shape
         np.testing.assert_allclose(got, want_wave, rtol=0, atol=2e-7)             # the gain is one fp32 multiply either way
+
+
+@pytest.mark.skipif(not R.reference_available(), reason="reference tree only exists in the build container")
+def test_sample_prologue_fuzz_vs_the_real_cfm_sample(tiny):
+    """`api.CFM._prepare` (the host half of `CFM.sample`, cfm.py:100-186) against the REAL reference method with a recording stub
+    in place of its transformer: 60 seeded random calls (batch 1-4, `lens` given or not, int / tensor durations incl. values
+    below lens + 1 and above `max_duration`, -1-padded text rows longer or shorter than the prompt, optional `edit_mask`, seeded
+    noise).  What the reference hands its transformer at the first evaluation — x = y0, the masked `step_cond`, the row mask — must
+    be what the product's per-utterance inputs describe."""
+    from types import SimpleNamespace
+    from tts_indic_server_f5_b200.api import CFM
+    cfg, sd = tiny[0], tiny[2]
+    cfm = R.build_reference_cfm(sd, cfg, None)
+    seen = {}
+
+    class Recorder(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.p = torch.nn.Parameter(torch.zeros(1))            # CFM.sample reads the model dtype off its first parameter
+
+        def forward(self, x, cond, text, time, mask, drop_audio_cond, drop_text):
+            if not seen:
+                seen.update(x=x.clone(), cond=cond.clone(), text=text.clone(), mask=None if mask is None else mask.clone())
+            return torch.zeros_like(x)
+
+    cfm.transformer = Recorder()
+    stub = SimpleNamespace(vocab_char_map=None, num_channels=cfg.mel_dim, _device="cpu")
+    g = torch.Generator().manual_seed(21)
+    ri = lambda lo, hi: int(torch.randint(lo, hi + 1, (1,), generator=g))  # noqa: E731
+    ran = 0
+    for case in range(60):
+        b, F_ = ri(1, 4), ri(5, 40)
+        cond = torch.randn(b, F_, cfg.mel_dim, generator=g)
+        nt = ri(1, 60)
+        text = torch.randint(0, cfg.vocab_size, (b, nt), generator=g)
+        for i in range(b):
+            text[i, ri(1, nt):] = -1
+        lens = None if ri(0, 1) else torch.tensor([ri(1, F_) for _ in range(b)])
+        max_dur = ri(30, 90)
+        duration = ri(1, 120) if ri(0, 1) else torch.tensor([ri(1, 120) for _ in range(b)])
+        edit_mask = None
+        if ri(0, 2) == 0:
+            edit_mask = torch.rand(b, F_ if lens is None else int(max(int(lens.max()), int((text != -1).sum(-1).max()))), generator=g) > 0.3
+        seed = ri(0, 1000)
+        seen.clear()
+        try:
+            out, _ = cfm.sample(cond=cond, text=text.clone(), duration=duration, lens=None if lens is None else lens.clone(), steps=1,
+                                cfg_strength=2.0, sway_sampling_coef=-1.0, seed=seed, max_duration=max_dur, edit_mask=edit_mask)
+        except RuntimeError:
+            continue                      # shapes the reference itself cannot broadcast (edit_mask narrower than its cond_mask, cond longer than max_duration)
+        ran += 1
+        utts = CFM._prepare(stub, cond, text.clone(), duration, lens, seed, max_dur, edit_mask, None)
+        assert len(utts) == b
+        N = seen["x"].shape[1]
+        for i, u in enumerate(utts):
+            n_ref = N if seen["mask"] is None else int(seen["mask"][i].sum())
+            assert u.n == n_ref, (case, i)
+            assert torch.equal(u.y0, seen["x"][i, :u.n]), (case, i)                   # the seeded CPU draw, per item
+            assert (seen["x"][i, u.n:] == 0).all()
+            assert torch.equal(u.text_ids, text[i][text[i] != -1])
+            # step_cond as the engine builds it from (cond, cond_len, edit_mask): engine.upload
+            m = torch.zeros(u.n, dtype=torch.bool)
+            m[: min(u.cond_len, u.n)] = True
+            if u.edit_mask is not None:
+                em = u.edit_mask.bool()[: u.n]
+                m[: em.numel()] &= em
+            c = torch.zeros(u.n, cfg.mel_dim)
+            k = min(u.cond.shape[0], u.n)
+            c[:k] = u.cond[:k]
+            assert torch.equal(torch.where(m[:, None], c, torch.zeros_like(c)), seen["cond"][i, :u.n]), (case, i)
+            assert (seen["cond"][i, u.n:] == 0).all()
+    print(f"prologue fuzz: {ran} of 60 calls accepted by the reference")
+    assert ran >= 40
