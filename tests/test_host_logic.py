@@ -558,3 +558,24 @@ def test_shard_plan_fuzz_covers_every_utterance_once():
         assert sorted(i for part in plan["parts"] for i in part) == list(range(n))
         for r in range(w):
             assert sorted(j for pk in plan["packs"][r] for j in pk) == list(range(len(plan["parts"][r])))
+
+
+def test_load_vocoder_reads_the_local_checkpoint_layout(tmp_path, monkeypatch):
+    """`load_vocoder("vocos", is_local=True, local_path=...)` (utils_infer.py:100-115): `pytorch_model.bin` of
+    charactr/vocos-mel-24khz carries the feature extractor's buffers next to backbone / head; the architecture is inferred from the
+    tensors (dim 512, intermediate 1536, 8 layers), extra keys are ignored, bigvgan is refused.  The engine itself needs a B200,
+    so it is replaced by a recorder here."""
+    from tts_indic_server_f5_b200 import api
+    sd = W.make_vocos_state_dict(W.VOCOS_24K, seed=3)
+    extra = {"feature_extractor.mel_spec.spectrogram.window": torch.hann_window(1024),
+             "feature_extractor.mel_spec.mel_scale.fb": torch.zeros(513, 100)}
+    torch.save({**sd, **extra}, str(tmp_path / "pytorch_model.bin"))
+    seen = {}
+    monkeypatch.setattr(api, "Vocos", lambda state_dict, cfg, device, precision="bf16": seen.update(sd=state_dict, cfg=cfg, device=device,
+                                                                                                  precision=precision) or "engine")
+    assert api.load_vocoder("vocos", is_local=True, local_path=str(tmp_path), device="cuda:0") == "engine"
+    assert (seen["cfg"].dim, seen["cfg"].intermediate_dim, seen["cfg"].num_layers) == (512, 1536, 8)
+    assert seen["cfg"] == W.VOCOS_24K and seen["device"] == "cuda:0" and seen["precision"] == "bf16"
+    assert all(torch.equal(seen["sd"][k], v) for k, v in sd.items())
+    with pytest.raises(NotImplementedError):
+        api.load_vocoder("bigvgan")
