@@ -348,3 +348,18 @@ def test_sample_prologue_fuzz_vs_the_real_cfm_sample(tiny):
             assert (seen["cond"][i, u.n:] == 0).all()
     print(f"prologue fuzz: {ran} of 60 calls accepted by the reference")
     assert ran >= 40
+
+
+@pytest.mark.skipif(not R.reference_available(), reason="reference tree only exists in the build container")
+def test_get_tokenizer_on_the_vendored_vocab_file():
+    """`get_tokenizer(path, "custom")` (model/utils.py:124-129) on the vocab file the reference ships
+    (`f5_tts/infer/examples/vocab.txt`): same map and size as the reference's own function; then ids of mixed Indic text through
+    both `list_str_to_idx` implementations with that map (characters outside the file fall back to 0)."""
+    ref = R.load_reference()
+    path = os.path.join(R.REFERENCE_ROOT, "src", "server", "f5_tts", "infer", "examples", "vocab.txt")
+    got_map, got_size = T.get_tokenizer(path, "custom")
+    want_map, want_size = ref.model_utils.get_tokenizer(path, "custom")
+    assert got_size == want_size == 2545 and got_map == want_map
+    texts = [T.synthetic_indic_text(50, s, script) + ", abc 12?" for s, script in ((1, "kannada"), (2, "devanagari"))]
+    toks = T.convert_char_to_pinyin(texts)
+    assert torch.equal(T.list_str_to_idx(toks, got_map), ref.model_utils.list_str_to_idx(toks, want_map))
