@@ -363,3 +363,47 @@ def test_get_tokenizer_on_the_vendored_vocab_file():
     texts = [T.synthetic_indic_text(50, s, script) + ", abc 12?" for s, script in ((1, "kannada"), (2, "devanagari"))]
     toks = T.convert_char_to_pinyin(texts)
     assert torch.equal(T.list_str_to_idx(toks, got_map), ref.model_utils.list_str_to_idx(toks, want_map))
+
+
+@pytest.mark.skipif(not R.reference_available(), reason="reference tree only exists in the build container")
+def test_boundary_signatures_match_the_reference_source():
+    """Drop-in surface, checked against the reference's SOURCE (parsed, not imported: `core/managers.py` pulls in the LLM stack):
+    `TTSManager` has the reference's methods with the reference's positional parameters, its instance attributes `device_type`,
+    `model`, `repo_id` and the same error for an unloaded model; `infer_process`, `infer_batch_process`, `load_model`,
+    `load_vocoder`, `preprocess_ref_audio_text`, `chunk_text` accept every parameter of the reference's functions under the
+    same names, in the same order (extra keyword-only additions come after them), with the same defaults for the sampler constants."""
+    import ast
+    import inspect
+    from tts_indic_server_f5_b200 import api
+    root = os.path.join(R.REFERENCE_ROOT, "src", "server")
+    mgr_src = ast.parse(open(os.path.join(root, "core", "managers.py"), encoding="utf-8").read())
+    cls = next(n for n in ast.walk(mgr_src) if isinstance(n, ast.ClassDef) and n.name == "TTSManager")
+    ref_methods = {f.name: [a.arg for a in f.args.args] for f in cls.body if isinstance(f, ast.FunctionDef)}
+    assert set(ref_methods) == {"__init__", "load", "synthesize"}
+    for name, params in ref_methods.items():
+        ours = list(inspect.signature(getattr(api.TTSManager, name)).parameters)
+        assert ours[: len(params)] == params, (name, ours, params)
+    attrs = {t.attr for n in ast.walk(cls) if isinstance(n, ast.Assign) for t in n.targets if isinstance(t, ast.Attribute)}
+    m = api.TTSManager(device_type="cuda")
+    assert attrs <= set(vars(m)) and m.model is None and m.repo_id == "ai4bharat/IndicF5" and m.device_type == "cuda"
+    with pytest.raises(ValueError, match="TTS model not loaded"):
+        m.synthesize("x", ref_audio_path="p", ref_text="r")
+    ui_src = ast.parse(open(os.path.join(root, "f5_tts", "infer", "utils_infer.py"), encoding="utf-8").read())
+    ref_fns = {n.name: n for n in ui_src.body if isinstance(n, ast.FunctionDef)}
+    consts = {t.id: ast.literal_eval(n.value) for n in ui_src.body if isinstance(n, ast.Assign) for t in n.targets
+              if isinstance(t, ast.Name) and isinstance(n.value, (ast.Constant, ast.UnaryOp))}
+    for k in ("target_sample_rate", "n_mel_channels", "hop_length", "win_length", "n_fft", "mel_spec_type", "target_rms",
+              "cross_fade_duration", "ode_method", "nfe_step", "cfg_strength", "sway_sampling_coef", "speed", "fix_duration"):
+        assert getattr(api, k) == consts[k], k                                # utils_infer.py:40-53
+    for name in ("infer_process", "infer_batch_process", "load_model", "load_vocoder", "preprocess_ref_audio_text", "chunk_text"):
+        want = [a.arg for a in ref_fns[name].args.args]
+        fn = getattr(api, name, None) or getattr(T, name)
+        got = list(inspect.signature(fn).parameters)
+        assert got[: len(want)] == want, (name, got, want)
+    cfm_src = ast.parse(open(os.path.join(root, "f5_tts", "model", "cfm.py"), encoding="utf-8").read())
+    sample = next(n for n in ast.walk(cfm_src) if isinstance(n, ast.FunctionDef) and n.name == "sample")
+    ours = inspect.signature(api.CFM.sample).parameters
+    assert list(ours)[: len(sample.args.args)] == [a.arg for a in sample.args.args]          # self, cond, text, duration
+    for a_, d_ in zip(sample.args.kwonlyargs, sample.args.kw_defaults):                         # lens ... edit_mask, same defaults
+        assert a_.arg in ours and ours[a_.arg].kind is inspect.Parameter.KEYWORD_ONLY, a_.arg
+        assert ours[a_.arg].default == ast.literal_eval(d_), a_.arg
