@@ -579,3 +579,32 @@ def test_load_vocoder_reads_the_local_checkpoint_layout(tmp_path, monkeypatch):
     assert all(torch.equal(seen["sd"][k], v) for k, v in sd.items())
     with pytest.raises(NotImplementedError):
         api.load_vocoder("bigvgan")
+
+
+def test_layout_fuzz():
+    """`build_layout` on 200 seeded random batches (1 - 48 utterances of 1 - 4096 frames): rows padded to 128, both CFG halves
+    identical, every live row covered by exactly one attention query tile whose key range is its own utterance, gaps of at least
+    GAP dead rows around every utterance (the k = 31 conv halo and the depthwise window read zeros there), segment table in order."""
+    import random
+    rnd = random.Random(4)
+    for _ in range(200):
+        lens = [rnd.choice([1, 2, 127, 128, 129, 255, 256, 257, rnd.randint(1, 4096)]) for _ in range(rnd.randint(1, 48))]
+        L = build_layout(lens)
+        R = L.half_rows
+        assert R % 128 == 0 and L.rows == 2 * R and L.row_pos.numel() == 2 * R and L.lengths == lens
+        pos = L.row_pos[:R]
+        assert torch.equal(L.row_pos[R:], pos) and int((pos >= 0).sum()) == sum(lens) == L.real_tokens
+        prev_end = 0
+        for u, (s, n) in enumerate(zip(L.starts, lens)):
+            assert s - prev_end >= GAP and torch.equal(pos[s:s + n], torch.arange(n, dtype=torch.int32))
+            assert (pos[prev_end:s] == -1).all() and (L.row_utt[s:s + n] == u).all()
+            prev_end = s + n
+        assert (pos[prev_end:] == -1).all() and R - prev_end >= 0
+        cover = torch.zeros(2 * R, dtype=torch.int32)
+        for q0, kv0, kvl, qv in L.attn_tiles.tolist():
+            cover[q0:q0 + qv] += 1
+            assert kv0 <= q0 and q0 + qv <= kv0 + kvl and 1 <= qv <= 256
+            assert int(L.row_pos[kv0]) == 0 and int(L.row_pos[kv0 + kvl - 1]) == kvl - 1
+            assert kv0 + kvl == 2 * R or int(L.row_pos[kv0 + kvl]) == -1
+        assert torch.equal(cover, (L.row_pos >= 0).to(torch.int32))
+        assert L.seg_rows.tolist() == [[h + s, n] for h in (0, R) for s, n in zip(L.starts, lens)]
