@@ -407,3 +407,40 @@ def test_boundary_signatures_match_the_reference_source():
     for a_, d_ in zip(sample.args.kwonlyargs, sample.args.kw_defaults):                         # lens ... edit_mask, same defaults
         assert a_.arg in ours and ours[a_.arg].kind is inspect.Parameter.KEYWORD_ONLY, a_.arg
         assert ours[a_.arg].default == ast.literal_eval(d_), a_.arg
+
+
+@pytest.mark.skipif(not R.reference_available(), reason="reference tree only exists in the build container")
+def test_oracle_fuzz_vs_the_real_reference(tiny):
+    """The parity anchor itself, on 16 seeded random shapes: the reference's own `DiT.forward` (both CFG branches, random time) and
+    `CFM.sample` (text shorter / longer than the prompt, durations at the lens + 1 floor, `lens` shorter than the prompt, sway on /
+    off, 1 - 5 steps) against the restatement — bit for bit, trajectory included."""
+    cfg, _, sd, _ = tiny
+    cfm = R.build_reference_cfm(sd, cfg)
+    g = torch.Generator().manual_seed(17)
+    ri = lambda lo, hi: int(torch.randint(lo, hi + 1, (1,), generator=g))  # noqa: E731
+    with torch.inference_mode():
+        for case in range(16):
+            n, nt = ri(3, 160), ri(1, 180)
+            x, cond = torch.randn(1, n, cfg.mel_dim, generator=g), torch.randn(1, n, cfg.mel_dim, generator=g)
+            text = torch.randint(0, cfg.vocab_size, (1, nt), generator=g)
+            text[0, ri(1, nt):] = -1
+            t = torch.rand((), generator=g)
+            for drop in (False, True):
+                want = cfm.transformer(x=x, cond=cond, text=text, time=t, mask=None, drop_audio_cond=drop, drop_text=drop)
+                assert torch.equal(O.dit_forward(sd, cfg, x, cond, text, t, drop, drop), want), (case, drop)
+            F_ = ri(2, 60)
+            prompt = torch.randn(1, F_, cfg.mel_dim, generator=g)
+            dur, steps = ri(1, 140), ri(1, 5)
+            lens = None if ri(0, 1) else torch.tensor([ri(1, F_)])
+            sway = -1.0 if ri(0, 1) else None
+            seed = ri(0, 99)
+            want, want_traj = cfm.sample(cond=prompt, text=text.clone(), duration=dur, lens=None if lens is None else lens.clone(), steps=steps,
+                                         cfg_strength=2.0, sway_sampling_coef=sway, seed=seed)
+            got, traj = O.cfm_sample(sd, cfg, prompt, text, dur, steps=steps, sway_sampling_coef=sway, seed=seed, lens=lens,
+                                     return_trajectory=True)
+            assert torch.equal(got, want) and torch.equal(traj, want_traj), case
+        modules = R.load_reference().modules                       # prompt mel (model/modules.py:75-101) at random lengths / levels
+        for k in range(6):
+            wave_ = torch.randn(ri(1, 2), ri(600, 60000), generator=g) * (10.0 ** -ri(0, 3))
+            want = modules.get_vocos_mel_spectrogram(wave_)
+            assert torch.equal(O.mel_spectrogram(wave_), want), k
